@@ -1,0 +1,181 @@
+/* ls2fm.h -- C ABI of libls2fm_sm100.so
+ *
+ * B200-native (sm_100a) replacement for the two native dependencies the Level-S2fM
+ * hot path sits on -- tiny-cuda-nn's hash-grid encoding (reference call sites
+ * models/base.py:17,37) and vren's ray/AABB test (utils/custom_functions.py:31) --
+ * plus the fused per-sample / per-ray kernels that replace the eager PyTorch graph of
+ * models/Renderer.py:51-116, models/SDF.py:55-226 and models/RadF.py:66-86.
+ *
+ * Conventions:
+ *  - plain C, no torch types; every pointer marked "device" is a CUDA device pointer
+ *    owned by the caller (PyTorch); the library never allocates or frees device memory
+ *    and keeps no global state besides a thread-local error string;
+ *  - every entry point is asynchronous on the given cudaStream_t (passed as void*),
+ *    performs no host synchronisation and is re-entrant across streams;
+ *  - return value 0 = success, non-zero = error (message via ls2fm_last_error());
+ *  - all arrays are contiguous, row-major, fp32 unless stated; "nullable" pointers may
+ *    be NULL to skip that output / input.
+ */
+#ifndef LS2FM_H_
+#define LS2FM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LS2FM_ABI_VERSION 1
+#define LS2FM_MAX_LEVELS 16
+#define LS2FM_MAX_LAYERS 4   /* linear layers of the geometry MLP: 1..3 hidden (width 64) + output */
+#define LS2FM_HIDDEN 64
+#define LS2FM_MAX_OUT 20     /* k_geo + 1 <= 20 */
+#define LS2FM_MAX_RAD_IN 68  /* 3 + 3 + 27 + 16 (+16 dual) rounded up to a multiple of 4 */
+
+/* One level of the multiresolution hash grid (tiny-cuda-nn GridEncoding). */
+typedef struct {
+    float scale;          /* exp2f(l*log2f(b))*N_min - 1 */
+    uint32_t resolution;  /* ceilf(scale)+1 */
+    uint32_t offset;      /* first entry of this level in the table (entries, not floats) */
+    uint32_t size;        /* entries in this level (hashmap_size) */
+    uint32_t hashed;      /* 1: prime-xor hash, 0: dense strides */
+} ls2fm_level_t;
+
+/* Hash-grid configuration as the reference builds it (models/base.py:130-139). */
+typedef struct {
+    int32_t n_levels;
+    int32_t n_features;        /* must be 2 */
+    int32_t log2_hashmap_size;
+    int32_t base_resolution;
+    float per_level_scale;
+} ls2fm_grid_cfg_t;
+
+/* A hash-grid + geometry-MLP field: SDF (models/SDF.py:41-53) or RadF's Geo_enc
+ * (models/RadF.py:28-45).
+ * theta packs the EFFECTIVE (weight-normalised) MLP parameters, layer after layer:
+ *   for l in 0..n_layers-1:  Wt_l [dims[l]][dims[l+1]]  (= W_l transposed, row-major),  b_l [dims[l+1]]
+ * dims[0] = 3 + 2*n_levels; hidden dims must be 64; dims[n_layers] = k_geo+1 <= 20. */
+typedef struct {
+    const float* table;   /* device, [n_entries*2] -- embed_fn.embedder_obj.params */
+    const float* theta;   /* device, packed as above */
+    int32_t n_levels;
+    ls2fm_level_t levels[LS2FM_MAX_LEVELS];
+    float bound_min[3];
+    float bound_max[3];
+    float rescale;        /* opt.SDF.VolSDF.rescale: enc[0:3] = x / rescale */
+    int32_t n_layers;
+    int32_t dims[LS2FM_MAX_LAYERS + 1];
+    float softplus_beta;       /* 100 */
+    float softplus_threshold;  /* 20 */
+    float sdf_sign;       /* +1 when opt.data.inside else -1:  sdf = sdf_sign * (y0 / scale_mlp) */
+    float scale_mlp;      /* opt.SDF.NN_Init.scale_mlp */
+} ls2fm_field_t;
+
+/* Where the sample points come from. */
+typedef struct {
+    const float* xyz;     /* device [n,3] explicit points, or NULL for ray mode */
+    const float* center;  /* device [n_rays,3]  (ray mode) */
+    const float* ray;     /* device [n_rays,3]  un-normalised direction (ray mode) */
+    const float* t;       /* device [n_rays,n_per_ray] depths; x = center + ray*t (mul then add, as torch) */
+    const int32_t* ray_index; /* device [n_rays] nullable: compacted list of ray ids to process (ray mode) */
+    const int32_t* n_active;  /* device scalar nullable: number of valid entries in ray_index */
+    int64_t n;            /* explicit mode: number of points; ray mode: n_rays * n_per_ray */
+    int32_t n_rays;
+    int32_t n_per_ray;
+    int32_t t_stride;     /* row stride of t (>= n_per_ray) */
+    int32_t t_offset;     /* first column of t to use */
+} ls2fm_points_t;
+
+/* The radiance decoder (models/base.py:221-261).  The reference applies NO hidden
+ * activation (len(self.mlp) is taken on an empty ModuleList, base.py:230,257), so the
+ * decoder is affine o sigmoid; the host composes W_eff = W3 W2 W1, b_eff accordingly
+ * and the kernel evaluates rgb = sigmoid(W_eff . in + b_eff),
+ * in = [x(3), normal(3), fourier(ray)(3+6*n_freq), geo(k_geo) (, geo2(k_geo))]  (Renderer.py:75). */
+typedef struct {
+    const float* w_eff;   /* device [3][in_dim] */
+    const float* b_eff;   /* device [3] */
+    int32_t in_dim;
+    int32_t n_freq;       /* 4 */
+    int32_t k_geo;        /* 16 */
+    int32_t k_geo2;       /* 0 or 16 (dual_field) */
+    const float* geo2;    /* device [n, k_geo2+1] nullable: RadF.Geometry_feat output (column 0 dropped) */
+} ls2fm_radiance_t;
+
+/* ------------------------------------------------------------------ host helpers */
+int ls2fm_abi_version(void);
+const char* ls2fm_last_error(void);
+/* fills levels[0..n_levels) and *n_entries; shared table for oracle and kernels */
+int ls2fm_grid_meta(const ls2fm_grid_cfg_t* cfg, ls2fm_level_t* levels, uint32_t* n_entries);
+/* dynamic shared memory (bytes) the fused kernels need for this field; 0 if unsupported */
+int ls2fm_smem_bytes(const ls2fm_field_t* field, int backward, int with_radiance);
+
+/* ------------------------------------------------------------------ vren replacement
+ * replaces vren.ray_aabb_intersect (utils/custom_functions.py:31) for N_voxels = 1, max_hits = 1.
+ * hits_t [m,2] = (max(t1,0), t2) or (-1,-1); hit_cnt [m] int32 nullable. */
+int ls2fm_ray_aabb(const float* rays_o, const float* rays_d, int64_t m,
+                   const float center[3], const float half_size[3],
+                   float* hits_t, int32_t* hit_cnt, void* stream);
+
+/* ------------------------------------------------------------------ tcnn replacement (unfused)
+ * replaces tcnn.Encoding.forward (models/base.py:37): u [m,3] -> enc [m, 2*n_levels].
+ * idx (nullable) [m, n_levels, 8] uint32 receives the table entry index of every corner
+ * (offset included) -- the bit-exact parity hook. */
+int ls2fm_grid_encode(const ls2fm_field_t* field, const float* u, int64_t m,
+                      float* enc, uint32_t* idx, void* stream);
+/* backward of the above: d_table += scatter(g_enc), d_u (nullable) [m,3] */
+int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64_t m,
+                               const float* g_enc, float* d_table, float* d_u, void* stream);
+
+/* ------------------------------------------------------------------ fused field evaluation
+ * replaces SDF.infer_sdf (+ SDF.gradient) / RadF.Geometry_feat (+ RadF.infer_app when rad != NULL).
+ *   out_y   [n, dout]  raw MLP output                                  (nullable)
+ *   out_sdf [n]        sign * (y0 / scale_mlp)                         (nullable)
+ *   out_nrm [n,3]      d(out_sdf)/dx  (analytic, reverse sweep)        (nullable)
+ *   out_rgb [n,3]      radiance (needs rad != NULL and ray mode)       (nullable) */
+int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts,
+                        const ls2fm_radiance_t* rad,
+                        float* out_y, float* out_sdf, float* out_nrm, float* out_rgb, void* stream);
+
+/* backward of ls2fm_field_forward.  Upstream gradients (all nullable): g_y [n,dout], g_sdf [n],
+ * g_nrm [n,3], g_rgb [n,3].  saved_nrm/saved_rgb: forward outputs (required when rad != NULL).
+ * Accumulates (+=, atomics) into d_table [n_entries*2], d_theta [len(theta)], d_w_eff [3*in_dim],
+ * d_b_eff [3]; writes d_geo2 [n,k_geo2+1]; each nullable.  The second-order path (gradient of the
+ * normals w.r.t. the parameters, SDF.gradient's create_graph=True) is included.  Gradients w.r.t. the
+ * sample positions are not produced: in the reference the only consumers of such a gradient sit behind
+ * vren's RayAABBIntersector, which defines no backward (utils/custom_functions.py:10-31). */
+int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts,
+                         const ls2fm_radiance_t* rad,
+                         const float* g_y, const float* g_sdf, const float* g_nrm, const float* g_rgb,
+                         const float* saved_nrm, const float* saved_rgb,
+                         float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
+                         void* stream);
+
+/* ------------------------------------------------------------------ compositing
+ * replaces SDF.sdf_to_sigma + Renderer.composite + the background tail of Renderer.forward
+ * (models/Renderer.py:33-49, 80-107).  Per ray: ray [R,3], t [R,N], sdf [R,N], rgbs [R,N,3],
+ * nrm [R,N,3]; beta_param = SDF.beta (device scalar), beta = exp(beta_param*beta_speed).
+ * Outputs rgb [R,3], depth [R], normal [R,3], opacity [R]. */
+int ls2fm_composite_forward(const float* ray, const float* t, const float* sdf, const float* rgbs,
+                            const float* nrm, const float* beta_param, float beta_speed,
+                            const float bgcolor[3], int32_t n_rays, int32_t n_samples,
+                            float* rgb, float* depth, float* normal, float* opacity, void* stream);
+/* upstream g_rgb [R,3], g_depth [R], g_normal [R,3] (nullable each) ->
+ * d_sdf [R,N], d_rgbs [R,N,3], d_nrm [R,N,3] (written), d_beta_param (+=, scalar), d_ray [R,3] (+=, nullable) */
+int ls2fm_composite_backward(const float* ray, const float* t, const float* sdf, const float* rgbs,
+                             const float* nrm, const float* beta_param, float beta_speed,
+                             const float bgcolor[3], int32_t n_rays, int32_t n_samples,
+                             const float* g_rgb, const float* g_depth, const float* g_normal,
+                             float* d_sdf, float* d_rgbs, float* d_nrm, float* d_beta_param, float* d_ray,
+                             void* stream);
+
+/* ------------------------------------------------------------------ depth samplers
+ * Renderer.sample_depth after the AABB test (models/Renderer.py:118-127,178-185):
+ * t[r,i] = (i+0.5)/N * (t_far - t_near) + t_near.  hits_t [R,2] nullable output. */
+int ls2fm_sample_uniform(const float* center, const float* ray, int32_t n_rays, int32_t n_samples,
+                         const float bound_min[3], const float bound_max[3],
+                         float* t, float* hits_t, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LS2FM_H_ */

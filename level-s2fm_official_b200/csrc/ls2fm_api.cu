@@ -1,0 +1,271 @@
+// ls2fm_api.cu -- the C ABI of libls2fm_sm100.so (include/ls2fm.h): argument checking + kernel launches.
+// Built by nvcc for sm_100a (see level-s2fm_official_b200/build.py).  No host synchronisation, no device
+// allocation, no global state besides a thread-local error string and the cached SM count.
+#include <stdio.h>
+
+#include <string>
+
+#include "ls2fm_field.cuh"
+#include "ls2fm_render.cuh"
+
+static thread_local std::string g_err;
+
+static int ls_fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+
+#if defined(LS_HOSTSIM)
+static int ls_sm_count() { return 2; }
+static int ls_max_smem() { return 227 * 1024; }
+template <class K> static int ls_opt_in_smem(K, int) { return 0; }
+static int ls_check_launch(const char*) { return 0; }
+#else
+static int ls_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+static int ls_max_smem() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (n <= 0) n = 48 * 1024;
+    }
+    return n;
+}
+template <class K> static int ls_opt_in_smem(K kernel, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return ls_fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    return 0;
+}
+static int ls_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return ls_fail(std::string(what) + ": " + cudaGetErrorString(e));
+    return 0;
+}
+#endif
+
+static int ls_check_field(const ls2fm_field_t* f) {
+    if (!f) return ls_fail("field is NULL");
+    if (!f->table || !f->theta) return ls_fail("field.table / field.theta is NULL");
+    if (f->n_levels < 1 || f->n_levels > LS2FM_MAX_LEVELS) return ls_fail("field.n_levels out of range (1..16)");
+    if (f->n_layers < 2 || f->n_layers > LS2FM_MAX_LAYERS) return ls_fail("field.n_layers out of range (2..4)");
+    if (f->dims[0] != 3 + 2 * f->n_levels) return ls_fail("field.dims[0] must be 3 + 2*n_levels");
+    for (int l = 1; l < f->n_layers; ++l)
+        if (f->dims[l] != LS2FM_HIDDEN) return ls_fail("hidden width must be 64");
+    if (f->dims[f->n_layers] < 1 || f->dims[f->n_layers] > LS2FM_MAX_OUT) return ls_fail("output width must be 1..20");
+    if (!(f->scale_mlp != 0.f)) return ls_fail("field.scale_mlp must be non-zero");
+    for (int d = 0; d < 3; ++d)
+        if (!(f->bound_max[d] > f->bound_min[d])) return ls_fail("field bounds are empty");
+    return 0;
+}
+
+static int ls_check_points(const ls2fm_points_t* p) {
+    if (!p) return ls_fail("points is NULL");
+    if (p->n < 0) return ls_fail("points.n < 0");
+    if (!p->xyz) {
+        if (!p->center || !p->ray || !p->t) return ls_fail("ray mode needs center, ray and t");
+        if (p->n_per_ray <= 0 || p->n_rays < 0) return ls_fail("ray mode needs n_per_ray > 0");
+        if (p->n != (int64_t)p->n_rays * p->n_per_ray) return ls_fail("points.n != n_rays * n_per_ray");
+        if (p->t_stride < p->n_per_ray + p->t_offset) return ls_fail("points.t_stride too small");
+    }
+    return 0;
+}
+
+static int ls_check_rad(const ls2fm_radiance_t* r, const ls2fm_field_t* f, const ls2fm_points_t* p) {
+    if (!r->w_eff || !r->b_eff) return ls_fail("radiance.w_eff / b_eff is NULL");
+    if (r->in_dim != 6 + 3 + 6 * r->n_freq + r->k_geo + r->k_geo2) return ls_fail("radiance.in_dim inconsistent");
+    if (r->in_dim > LS2FM_MAX_RAD_IN) return ls_fail("radiance.in_dim too large");
+    if (r->k_geo != f->dims[f->n_layers] - 1) return ls_fail("radiance.k_geo must equal field output width - 1");
+    if (r->k_geo2 > 0 && !r->geo2) return ls_fail("radiance.geo2 is NULL but k_geo2 > 0");
+    if (!p->ray || p->n_per_ray <= 0) return ls_fail("radiance needs the ray directions (points.ray, n_per_ray)");
+    return 0;
+}
+
+static void ls_fill_args(LsFieldArgs& a, const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad) {
+    memset(&a, 0, sizeof(a));
+    a.f = *field;
+    a.p = *pts;
+    if (rad) a.r = *rad;
+    for (int d = 0; d < 3; ++d) a.inv_ext[d] = 1.0f / (field->bound_max[d] - field->bound_min[d]);
+    a.s = field->sdf_sign / field->scale_mlp;
+}
+
+extern "C" {
+
+int ls2fm_abi_version(void) { return LS2FM_ABI_VERSION; }
+
+const char* ls2fm_last_error(void) { return g_err.c_str(); }
+
+int ls2fm_grid_meta(const ls2fm_grid_cfg_t* cfg, ls2fm_level_t* levels, uint32_t* n_entries) {
+    if (!cfg || !levels) return ls_fail("grid_meta: NULL argument");
+    if (cfg->n_levels < 1 || cfg->n_levels > LS2FM_MAX_LEVELS) return ls_fail("grid_meta: n_levels out of range");
+    if (cfg->n_features != 2) return ls_fail("grid_meta: n_features_per_level must be 2");
+    // tiny-cuda-nn GridEncoding constructor [EXT]: float32 arithmetic throughout
+    const float log2b = log2f(cfg->per_level_scale);
+    uint32_t offset = 0;
+    for (int l = 0; l < cfg->n_levels; ++l) {
+        const float scale = exp2f((float)l * log2b) * (float)cfg->base_resolution - 1.0f;
+        const uint32_t res = (uint32_t)ceilf(scale) + 1u;
+        const uint32_t max_params = UINT32_MAX / 2u;
+        uint32_t params = powf((float)res, 3.0f) > (float)max_params ? max_params : res * res * res;
+        params = (params + 7u) / 8u * 8u;
+        const uint32_t cap = 1u << cfg->log2_hashmap_size;
+        if (params > cap) params = cap;
+        uint32_t stride = 1;
+        for (int d = 0; d < 3 && stride <= params; ++d) stride *= res;
+        levels[l].scale = scale;
+        levels[l].resolution = res;
+        levels[l].offset = offset;
+        levels[l].size = params;
+        levels[l].hashed = params < stride ? 1u : 0u;
+        offset += params;
+    }
+    if (n_entries) *n_entries = offset;
+    return 0;
+}
+
+int ls2fm_smem_bytes(const ls2fm_field_t* field, int backward, int with_radiance) {
+    if (!field || field->n_layers < 2 || field->n_layers > LS2FM_MAX_LAYERS) return 0;
+    const LsNet n = ls_plan_net(*field, with_radiance ? LS2FM_MAX_RAD_IN : 0, backward ? LS_BW_WARPS : 4, backward != 0);
+    return n.total * (int)sizeof(float);
+}
+
+int ls2fm_ray_aabb(const float* rays_o, const float* rays_d, int64_t m, const float center[3], const float half_size[3],
+                   float* hits_t, int32_t* hit_cnt, void* stream) {
+    if (m < 0 || (m > 0 && (!rays_o || !rays_d || !hits_t))) return ls_fail("ray_aabb: bad arguments");
+    if (m == 0) return 0;
+    const int bs = 256;
+    LS_LAUNCH(ls_ray_aabb_kernel, (unsigned)((m + bs - 1) / bs), bs, 0, stream, rays_o, rays_d, m, center[0], center[1],
+              center[2], half_size[0], half_size[1], half_size[2], hits_t, hit_cnt);
+    return ls_check_launch("ray_aabb");
+}
+
+int ls2fm_sample_uniform(const float* center, const float* ray, int32_t n_rays, int32_t n_samples, const float bound_min[3],
+                         const float bound_max[3], float* t, float* hits_t, void* stream) {
+    if (n_rays < 0 || n_samples <= 0 || (n_rays > 0 && (!center || !ray || !t))) return ls_fail("sample_uniform: bad arguments");
+    if (n_rays == 0) return 0;
+    // center / half size as models/Renderer.py:18-19: (max+min)/2, (max-min)/2
+    float c[3], h[3];
+    for (int d = 0; d < 3; ++d) { c[d] = (bound_max[d] + bound_min[d]) / 2.f; h[d] = (bound_max[d] - bound_min[d]) / 2.f; }
+    const int wpb = 8;
+    LS_LAUNCH(ls_sample_uniform_kernel, (unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, 0, stream, center, ray, n_rays, n_samples,
+              c[0], c[1], c[2], h[0], h[1], h[2], t, hits_t);
+    return ls_check_launch("sample_uniform");
+}
+
+int ls2fm_grid_encode(const ls2fm_field_t* field, const float* u, int64_t m, float* enc, uint32_t* idx, void* stream) {
+    if (!field || !field->table) return ls_fail("grid_encode: field/table is NULL");
+    if (field->n_levels < 1 || field->n_levels > LS2FM_MAX_LEVELS) return ls_fail("grid_encode: n_levels out of range");
+    if (m < 0 || (m > 0 && !u)) return ls_fail("grid_encode: bad arguments");
+    if (m == 0) return 0;
+    const int bs = 256;
+    const int64_t total = m * field->n_levels;
+    LS_LAUNCH(ls_grid_encode_kernel, (unsigned)((total + bs - 1) / bs), bs, 0, stream, *field, u, m, enc, idx);
+    return ls_check_launch("grid_encode");
+}
+
+int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64_t m, const float* g_enc, float* d_table,
+                               float* d_u, void* stream) {
+    if (!field || !field->table) return ls_fail("grid_encode_backward: field/table is NULL");
+    if (field->n_levels < 1 || field->n_levels > LS2FM_MAX_LEVELS) return ls_fail("grid_encode_backward: n_levels out of range");
+    if (m < 0 || (m > 0 && (!u || !g_enc))) return ls_fail("grid_encode_backward: bad arguments");
+    if (m == 0) return 0;
+    const int bs = 256;
+    const int64_t total = m * field->n_levels;
+    LS_LAUNCH(ls_grid_encode_backward_kernel, (unsigned)((total + bs - 1) / bs), bs, 0, stream, *field, u, m, g_enc, d_table, d_u);
+    return ls_check_launch("grid_encode_backward");
+}
+
+int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, float* out_y,
+                        float* out_sdf, float* out_nrm, float* out_rgb, void* stream) {
+    if (ls_check_field(field) || ls_check_points(pts)) return 1;
+    if (rad && ls_check_rad(rad, field, pts)) return 1;
+    if (out_rgb && !rad) return ls_fail("field_forward: out_rgb needs the radiance block");
+    if (pts->n == 0) return 0;
+    LsFieldArgs a;
+    ls_fill_args(a, field, pts, rad);
+    a.out_y = out_y; a.out_sdf = out_sdf; a.out_nrm = out_nrm; a.out_rgb = out_rgb;
+    // as many warps per CTA as shared memory allows (one persistent CTA per SM)
+    int nw = 16;
+    const int64_t n_tiles = (pts->n + LS_WS - 1) / LS_WS;
+    for (;; nw -= 4) {
+        a.net = ls_plan_net(*field, rad ? rad->in_dim : 0, nw, false);
+        if (a.net.total * (int)sizeof(float) <= ls_max_smem()) break;
+        if (nw <= 4) return ls_fail("field_forward: network does not fit in shared memory");
+    }
+    const int smem = a.net.total * (int)sizeof(float);
+    if (ls_opt_in_smem(ls_field_forward_kernel, smem)) return 1;
+    int64_t grid = (n_tiles + nw - 1) / nw;
+    if (grid > ls_sm_count()) grid = ls_sm_count();
+    LS_LAUNCH(ls_field_forward_kernel, (unsigned)grid, nw * 32, smem, stream, a);
+    return ls_check_launch("field_forward");
+}
+
+int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
+                         const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
+                         const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
+                         void* stream) {
+    if (ls_check_field(field) || ls_check_points(pts)) return 1;
+    if (rad && ls_check_rad(rad, field, pts)) return 1;
+    if (rad && g_rgb && (!saved_nrm || !saved_rgb)) return ls_fail("field_backward: saved_nrm / saved_rgb required with radiance");
+    if (!rad && (g_rgb || d_w_eff || d_b_eff || d_geo2)) return ls_fail("field_backward: radiance gradients need the radiance block");
+    if (pts->n == 0) return 0;
+    LsFieldArgs a;
+    ls_fill_args(a, field, pts, (rad && g_rgb) ? rad : nullptr);
+    a.g_y = g_y; a.g_sdf = g_sdf; a.g_nrm = g_nrm; a.g_rgb = g_rgb;
+    a.saved_nrm = saved_nrm; a.saved_rgb = saved_rgb;
+    a.d_table = d_table; a.d_theta = d_theta; a.d_w_eff = d_w_eff; a.d_b_eff = d_b_eff; a.d_geo2 = d_geo2;
+    const bool with_rad = rad && g_rgb;
+    const bool tan = with_rad || g_nrm;
+    a.net = ls_plan_net(*field, with_rad ? rad->in_dim : 0, LS_BW_WARPS, true);
+    const int smem = a.net.total * (int)sizeof(float);
+    if (smem > ls_max_smem()) return ls_fail("field_backward: network does not fit in shared memory");
+    const int64_t n_ct = (pts->n + LS_WS * LS_BW_WARPS - 1) / (LS_WS * LS_BW_WARPS);
+    int64_t grid = n_ct < ls_sm_count() ? n_ct : ls_sm_count();
+    if (tan) {
+        if (ls_opt_in_smem(ls_field_backward_kernel<true>, smem)) return 1;
+        LS_LAUNCH(ls_field_backward_kernel<true>, (unsigned)grid, LS_BW_THREADS, smem, stream, a);
+    } else {
+        if (ls_opt_in_smem(ls_field_backward_kernel<false>, smem)) return 1;
+        LS_LAUNCH(ls_field_backward_kernel<false>, (unsigned)grid, LS_BW_THREADS, smem, stream, a);
+    }
+    return ls_check_launch("field_backward");
+}
+
+int ls2fm_composite_forward(const float* ray, const float* t, const float* sdf, const float* rgbs, const float* nrm,
+                            const float* beta_param, float beta_speed, const float bgcolor[3], int32_t n_rays, int32_t n_samples,
+                            float* rgb, float* depth, float* normal, float* opacity, void* stream) {
+    if (n_rays < 0 || n_samples < 2) return ls_fail("composite_forward: need n_samples >= 2");
+    if (n_rays > 0 && (!ray || !t || !sdf || !beta_param)) return ls_fail("composite_forward: NULL input");
+    if (n_rays == 0) return 0;
+    const int wpb = 4;
+    LS_LAUNCH(ls_composite_forward_kernel, (unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, 0, stream, ray, t, sdf, rgbs, nrm,
+              beta_param, beta_speed, bgcolor[0], bgcolor[1], bgcolor[2], n_rays, n_samples, rgb, depth, normal, opacity);
+    return ls_check_launch("composite_forward");
+}
+
+int ls2fm_composite_backward(const float* ray, const float* t, const float* sdf, const float* rgbs, const float* nrm,
+                             const float* beta_param, float beta_speed, const float bgcolor[3], int32_t n_rays, int32_t n_samples,
+                             const float* g_rgb, const float* g_depth, const float* g_normal, float* d_sdf, float* d_rgbs,
+                             float* d_nrm, float* d_beta_param, float* d_ray, void* stream) {
+    if (n_rays < 0 || n_samples < 2) return ls_fail("composite_backward: need n_samples >= 2");
+    if (n_samples - 1 > 32 * LS_MAX_CHUNKS) return ls_fail("composite_backward: at most 257 samples per ray");
+    if (n_rays > 0 && (!ray || !t || !sdf || !beta_param)) return ls_fail("composite_backward: NULL input");
+    if (n_rays == 0) return 0;
+    const int wpb = 4;
+    LS_LAUNCH(ls_composite_backward_kernel, (unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, 0, stream, ray, t, sdf, rgbs, nrm,
+              beta_param, beta_speed, bgcolor[0], bgcolor[1], bgcolor[2], n_rays, n_samples, g_rgb, g_depth, g_normal, d_sdf,
+              d_rgbs, d_nrm, d_beta_param, d_ray);
+    return ls_check_launch("composite_backward");
+}
+
+}  // extern "C"

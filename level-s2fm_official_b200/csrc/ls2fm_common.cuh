@@ -1,0 +1,134 @@
+// ls2fm_common.cuh -- shared definitions for the sm_100a kernels.
+//
+// The product library is built by nvcc for sm_100a only.  The same sources also compile with
+// g++ -DLS_HOSTSIM against tests/hostsim/simt.h (a fiber-based SIMT emulator) so that the
+// kernel arithmetic can be checked against the oracle in a container without a GPU; that is
+// test infrastructure -- the python package never loads it and there is no CPU product path.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/ls2fm.h"
+
+#if defined(LS_HOSTSIM)
+#include "../../tests/hostsim/simt.h"
+#define LS_HD inline
+#define LS_DEV inline
+#define LS_DYN_SMEM(name) float* name = reinterpret_cast<float*>(simt::S().smem)
+#define LS_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    simt::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#define LS_HD __host__ __device__ __forceinline__
+#define LS_DEV __device__ __forceinline__
+#define LS_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
+#define LS_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
+
+// ---------------------------------------------------------------- constants
+constexpr int LS_H = LS2FM_HIDDEN;   // hidden width of the geometry MLP
+constexpr int LS_WS = 8;             // samples per warp tile
+constexpr int LS_EROWS = 36;         // rows of an encoding buffer (3 + 2*16 = 35 -> 36)
+constexpr int LS_OROWS = LS2FM_MAX_OUT;  // rows of an output buffer (17 -> 20)
+constexpr int LS_WPITCH = LS_H + 4;  // smem pitch of a [*, 64] weight matrix (== 4 mod 8: conflict-free rows)
+constexpr int LS_OPITCH = LS2FM_MAX_OUT; // smem pitch of the [64, dout] output layer (20 == 4 mod 8)
+
+// explicit single-rounding ops: the coordinate arithmetic must round exactly like the reference's
+// eager torch ops (mul, then add -- never contracted into an fma) so hash cells agree bit for bit
+LS_DEV float ls_fmul(float a, float b) { return __fmul_rn(a, b); }
+LS_DEV float ls_fadd(float a, float b) { return __fadd_rn(a, b); }
+LS_DEV float ls_fsub(float a, float b) { return __fsub_rn(a, b); }
+LS_DEV float ls_fdiv(float a, float b) { return __fdiv_rn(a, b); }
+LS_DEV float ls_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// ---------------------------------------------------------------- softplus (beta, threshold)
+// torch.nn.Softplus(beta=100, threshold=20) as the reference's Geometry MLP uses it (models/base.py:203).
+LS_DEV float ls_softplus(float z, float beta, float thr) {
+    const float bz = z * beta;
+    return bz > thr ? z : log1pf(expf(bz)) / beta;
+}
+// phi'(z) recovered from a = phi(z):  exp(-beta a) = 1/(1+exp(beta z))  =>  phi' = 1 - exp(-beta a).
+// In the threshold zone (a = z, beta z > 20) this gives 1 - 2e-9 == 1.0f, as autograd does.
+LS_DEV float ls_softplus_d1_from_a(float a, float beta) { return -expm1f(-beta * a); }
+LS_DEV float ls_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---------------------------------------------------------------- hash grid (tcnn GridEncoding) [EXT]
+struct LsCell {
+    uint32_t g[3];   // (uint32_t)(int)floorf(p)
+    float w[3];      // p - floorf(p)
+};
+
+LS_DEV LsCell ls_cell(float scale, const float u[3]) {
+    LsCell c;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float p = ls_fma(scale, u[d], 0.5f);
+        const float fl = floorf(p);
+        c.g[d] = (uint32_t)(int)fl;
+        c.w[d] = p - fl;
+    }
+    return c;
+}
+
+LS_DEV uint32_t ls_corner_index(uint32_t resolution, uint32_t size, uint32_t hashed, const LsCell& c, int corner) {
+    const uint32_t q0 = c.g[0] + (corner & 1), q1 = c.g[1] + ((corner >> 1) & 1), q2 = c.g[2] + ((corner >> 2) & 1);
+    uint32_t index;
+    if (hashed) {
+        index = q0 ^ (q1 * 2654435761u) ^ (q2 * 805459861u);
+    } else {
+        // dense level: all three strides fit (that is what hashed == 0 means); uint32 wrap as in tcnn
+        index = q0 + q1 * resolution + q2 * resolution * resolution;
+    }
+    return index % size;
+}
+
+// world -> unit cube exactly as models/base.py:35: (x - bmin) / (bmax - bmin)
+LS_DEV void ls_world_to_unit(const float bmin[3], const float bmax[3], const float x[3], float u[3]) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) u[d] = ls_fdiv(ls_fsub(x[d], bmin[d]), ls_fsub(bmax[d], bmin[d]));
+}
+
+// ---------------------------------------------------------------- ray / AABB (vren) [EXT]
+// t_near/t_far of the slab test; (-1,-1) on a miss.  Mirrors oracle/aabb.py.
+LS_DEV void ls_ray_aabb(const float o[3], const float d[3], const float center[3], const float half[3],
+                        float* t_near, float* t_far) {
+    float t1 = -INFINITY, t2 = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float inv = ls_fdiv(1.0f, d[k]);
+        const float lo = ls_fmul(ls_fsub(ls_fsub(center[k], half[k]), o[k]), inv);
+        const float hi = ls_fmul(ls_fsub(ls_fadd(center[k], half[k]), o[k]), inv);
+        t1 = fmaxf(t1, fminf(lo, hi));
+        t2 = fminf(t2, fmaxf(lo, hi));
+    }
+    if (t1 <= t2 && t2 > 0.f) { *t_near = fmaxf(t1, 0.f); *t_far = t2; }
+    else { *t_near = -1.f; *t_far = -1.f; }
+}
+
+// Laplace-CDF density (models/SDF.py:84-87): sigma = alpha * (s >= 0 ? e : 1 - e), e = .5 exp(-|s|/beta)
+LS_DEV float ls_sdf_to_sigma(float s, float alpha, float beta) {
+    const float e = 0.5f * expf(-fabsf(s) / beta);
+    return alpha * (s >= 0.f ? e : 1.f - e);
+}
+
+// ---------------------------------------------------------------- theta layout
+// packed effective MLP parameters: for l: Wt_l [dims[l]][dims[l+1]] then b_l [dims[l+1]]
+struct LsThetaLayout {
+    int w_off[LS2FM_MAX_LAYERS];
+    int b_off[LS2FM_MAX_LAYERS];
+    int total;
+};
+inline LsThetaLayout ls_theta_layout(const ls2fm_field_t& f) {
+    LsThetaLayout t;
+    int off = 0;
+    for (int l = 0; l < LS2FM_MAX_LAYERS; ++l) { t.w_off[l] = 0; t.b_off[l] = 0; }
+    for (int l = 0; l < f.n_layers; ++l) {
+        t.w_off[l] = off; off += f.dims[l] * f.dims[l + 1];
+        t.b_off[l] = off; off += f.dims[l + 1];
+    }
+    t.total = off;
+    return t;
+}

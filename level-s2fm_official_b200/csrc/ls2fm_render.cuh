@@ -1,0 +1,287 @@
+// ls2fm_render.cuh -- per-ray kernels: ray/AABB clipping, uniform depth samples, Laplace-CDF density +
+// alpha compositing (forward and backward), and the unfused hash-grid encoding (tcnn replacement).
+//
+// Reference: vren.ray_aabb_intersect [EXT] via utils/custom_functions.py:10-31; Renderer.sample_depth
+// (models/Renderer.py:118-127); SDF.sdf_to_sigma (models/SDF.py:84-87); Renderer.composite
+// (models/Renderer.py:33-49) and the background tail of Renderer.forward (Renderer.py:88-107).
+#pragma once
+
+#include "ls2fm_common.cuh"
+
+constexpr int LS_MAX_CHUNKS = 8;   // compositing: up to 8 * 32 = 256 samples per ray
+
+// ---------------------------------------------------------------- ray / AABB
+__global__ void ls_ray_aabb_kernel(const float* __restrict__ o, const float* __restrict__ d, int64_t m,
+                                   float cx, float cy, float cz, float hx, float hy, float hz,
+                                   float* __restrict__ hits_t, int32_t* __restrict__ hit_cnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float oo[3] = {o[3 * i], o[3 * i + 1], o[3 * i + 2]};
+    const float dd[3] = {d[3 * i], d[3 * i + 1], d[3 * i + 2]};
+    const float c[3] = {cx, cy, cz}, h[3] = {hx, hy, hz};
+    float tn, tf;
+    ls_ray_aabb(oo, dd, c, h, &tn, &tf);
+    hits_t[2 * i] = tn;
+    hits_t[2 * i + 1] = tf;
+    if (hit_cnt) hit_cnt[i] = tf > 0.f ? 1 : 0;
+}
+
+// ---------------------------------------------------------------- uniform mid-point samples
+// t[r,i] = (i + 0.5) / N * (t_far - t_near) + t_near with torch's rounding sequence (div, mul, add).
+__global__ void ls_sample_uniform_kernel(const float* __restrict__ center, const float* __restrict__ ray, int n_rays,
+                                         int n_samples, float cx, float cy, float cz, float hx, float hy, float hz,
+                                         float* __restrict__ t, float* __restrict__ hits_t) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;
+    const float oo[3] = {center[3 * r], center[3 * r + 1], center[3 * r + 2]};
+    const float dd[3] = {ray[3 * r], ray[3 * r + 1], ray[3 * r + 2]};
+    const float c[3] = {cx, cy, cz}, h[3] = {hx, hy, hz};
+    float tn, tf;
+    ls_ray_aabb(oo, dd, c, h, &tn, &tf);
+    if (hits_t && lane == 0) { hits_t[2 * r] = tn; hits_t[2 * r + 1] = tf; }
+    const float ext = ls_fsub(tf, tn);
+    for (int i = lane; i < n_samples; i += 32)
+        t[(int64_t)r * n_samples + i] = ls_fadd(ls_fmul(ls_fdiv((float)i + 0.5f, (float)n_samples), ext), tn);
+}
+
+// ---------------------------------------------------------------- warp scan helpers
+LS_DEV float ls_warp_incl_scan(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+LS_DEV float ls_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- compositing, forward
+// one warp per ray; lane l owns samples l, l+32, ...; transmittance by a warp-level exclusive
+// prefix sum of sigma*delta carried across the chunks.
+__global__ void ls_composite_forward_kernel(const float* __restrict__ ray, const float* __restrict__ t,
+                                            const float* __restrict__ sdf, const float* __restrict__ rgbs,
+                                            const float* __restrict__ nrm, const float* __restrict__ beta_param,
+                                            float beta_speed, float bg0, float bg1, float bg2, int n_rays, int N,
+                                            float* __restrict__ rgb, float* __restrict__ depth,
+                                            float* __restrict__ normal, float* __restrict__ opacity) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;
+    const float beta = expf(__ldg(beta_param) * beta_speed);
+    const float alpha = 1.f / beta;
+    const float rx = ray[3 * r], ry = ray[3 * r + 1], rz = ray[3 * r + 2];
+    const float rlen = sqrtf(rx * rx + ry * ry + rz * rz);
+    const float* tr = t + (int64_t)r * N;
+    const float* sr = sdf + (int64_t)r * N;
+    float carry = 0.f;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // rgb(3) depth(1) normal(3) opacity(1)
+    for (int base = 0; base < N - 1; base += 32) {
+        const int i = base + lane;
+        const bool on = i < N - 1;
+        float sd = 0.f, ti = 0.f;
+        if (on) {
+            ti = tr[i];
+            sd = ls_sdf_to_sigma(sr[i], alpha, beta) * ((tr[i + 1] - ti) * rlen);
+        }
+        const float incl = ls_warp_incl_scan(sd, lane);
+        const float T = expf(-(carry + incl - sd));
+        const float w = on ? T * (1.f - expf(-sd)) : 0.f;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (on) {
+            const int64_t k = (int64_t)r * N + i;
+            if (rgbs) { acc[0] += w * rgbs[3 * k]; acc[1] += w * rgbs[3 * k + 1]; acc[2] += w * rgbs[3 * k + 2]; }
+            acc[3] += w * ti;
+            if (nrm) { acc[4] += w * nrm[3 * k]; acc[5] += w * nrm[3 * k + 1]; acc[6] += w * nrm[3 * k + 2]; }
+            acc[7] += w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = ls_warp_sum(acc[k]);
+    if (lane == 0) {
+        const float op = acc[7], rem = 1.f - op;
+        const int64_t kl = (int64_t)r * N + (N - 1);
+        if (rgb) { rgb[3 * r] = acc[0] + rem * bg0; rgb[3 * r + 1] = acc[1] + rem * bg1; rgb[3 * r + 2] = acc[2] + rem * bg2; }
+        if (depth) depth[r] = acc[3] + rem * tr[N - 1];
+        if (normal && nrm) {
+            normal[3 * r] = acc[4] + rem * nrm[3 * kl]; normal[3 * r + 1] = acc[5] + rem * nrm[3 * kl + 1];
+            normal[3 * r + 2] = acc[6] + rem * nrm[3 * kl + 2];
+        }
+        if (opacity) opacity[r] = op;
+    }
+}
+
+// ---------------------------------------------------------------- compositing, backward
+// L = sum_i w_i (v_i - v_bg) + v_bg with v = <upstream, per-sample value>;  dL/d(sd_k) = c_k T_{k+1} - sum_{i>k} c_i w_i.
+__global__ void ls_composite_backward_kernel(const float* __restrict__ ray, const float* __restrict__ t,
+                                             const float* __restrict__ sdf, const float* __restrict__ rgbs,
+                                             const float* __restrict__ nrm, const float* __restrict__ beta_param,
+                                             float beta_speed, float bg0, float bg1, float bg2, int n_rays, int N,
+                                             const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
+                                             const float* __restrict__ g_normal, float* __restrict__ d_sdf,
+                                             float* __restrict__ d_rgbs, float* __restrict__ d_nrm,
+                                             float* __restrict__ d_beta_param, float* __restrict__ d_ray) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;
+    const float beta = expf(__ldg(beta_param) * beta_speed);
+    const float alpha = 1.f / beta;
+    const float rx = ray[3 * r], ry = ray[3 * r + 1], rz = ray[3 * r + 2];
+    const float rlen = sqrtf(rx * rx + ry * ry + rz * rz);
+    const float* tr = t + (int64_t)r * N;
+    const float* sr = sdf + (int64_t)r * N;
+    float gr[3] = {0.f, 0.f, 0.f}, gn[3] = {0.f, 0.f, 0.f}, gd = 0.f;
+    if (g_rgb) { gr[0] = g_rgb[3 * r]; gr[1] = g_rgb[3 * r + 1]; gr[2] = g_rgb[3 * r + 2]; }
+    if (g_normal) { gn[0] = g_normal[3 * r]; gn[1] = g_normal[3 * r + 1]; gn[2] = g_normal[3 * r + 2]; }
+    if (g_depth) gd = g_depth[r];
+    const int64_t kl = (int64_t)r * N + (N - 1);
+    float vbg = gr[0] * bg0 + gr[1] * bg1 + gr[2] * bg2 + gd * tr[N - 1];
+    if (nrm) vbg += gn[0] * nrm[3 * kl] + gn[1] * nrm[3 * kl + 1] + gn[2] * nrm[3 * kl + 2];
+
+    float w[LS_MAX_CHUNKS], cw[LS_MAX_CHUNKS], Tn[LS_MAX_CHUNKS], cc[LS_MAX_CHUNKS];
+    float carry = 0.f, Csum = 0.f, op = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < LS_MAX_CHUNKS; ++ch) {
+        w[ch] = cw[ch] = Tn[ch] = cc[ch] = 0.f;
+        if (ch * 32 < N - 1) {
+            const int i = ch * 32 + lane;
+            const bool on = i < N - 1;
+            float sd = 0.f, ti = 0.f;
+            if (on) {
+                ti = tr[i];
+                sd = ls_sdf_to_sigma(sr[i], alpha, beta) * ((tr[i + 1] - ti) * rlen);
+            }
+            const float incl = ls_warp_incl_scan(sd, lane);
+            const float T = expf(-(carry + incl - sd));
+            const float ex = expf(-sd);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+            if (on) {
+                const int64_t k = (int64_t)r * N + i;
+                float v = gd * ti;
+                if (rgbs) v += gr[0] * rgbs[3 * k] + gr[1] * rgbs[3 * k + 1] + gr[2] * rgbs[3 * k + 2];
+                if (nrm) v += gn[0] * nrm[3 * k] + gn[1] * nrm[3 * k + 1] + gn[2] * nrm[3 * k + 2];
+                w[ch] = T * (1.f - ex);
+                cc[ch] = v - vbg;
+                cw[ch] = cc[ch] * w[ch];
+                Tn[ch] = T * ex;
+                Csum += cw[ch];
+                op += w[ch];
+            }
+        }
+    }
+    Csum = ls_warp_sum(Csum);
+    op = ls_warp_sum(op);
+    float pre = 0.f;          // running inclusive prefix of c_i w_i
+    float dbeta = 0.f, drlen = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < LS_MAX_CHUNKS; ++ch) {
+        if (ch * 32 < N - 1) {
+            const int i = ch * 32 + lane;
+            const bool on = i < N - 1;
+            const float incl = ls_warp_incl_scan(cw[ch], lane);
+            const float S = Csum - (pre + incl);           // sum_{j>i} c_j w_j
+            pre += __shfl_sync(0xffffffffu, incl, 31);
+            if (on) {
+                const int64_t k = (int64_t)r * N + i;
+                const float dsd = cc[ch] * Tn[ch] - S;
+                const float s = sr[i];
+                const float dt = tr[i + 1] - tr[i];
+                const float e = 0.5f * expf(-fabsf(s) / beta);
+                const float sigma = alpha * (s >= 0.f ? e : 1.f - e);
+                const float dsigma = dsd * dt * rlen;
+                drlen += dsd * sigma * dt;
+                if (d_sdf) d_sdf[k] = dsigma * (-alpha * e / beta);
+                // d sigma / d beta = -sigma/beta + alpha * (+-) e |s| / beta^2
+                const float de = e * fabsf(s) / (beta * beta);
+                dbeta += dsigma * (-sigma / beta + alpha * (s >= 0.f ? de : -de));
+                if (d_rgbs) { d_rgbs[3 * k] = w[ch] * gr[0]; d_rgbs[3 * k + 1] = w[ch] * gr[1]; d_rgbs[3 * k + 2] = w[ch] * gr[2]; }
+                if (d_nrm) { d_nrm[3 * k] = w[ch] * gn[0]; d_nrm[3 * k + 1] = w[ch] * gn[1]; d_nrm[3 * k + 2] = w[ch] * gn[2]; }
+            }
+        }
+    }
+    if (lane == 0) {
+        const float rem = 1.f - op;
+        if (d_sdf) d_sdf[kl] = 0.f;
+        if (d_rgbs) { d_rgbs[3 * kl] = 0.f; d_rgbs[3 * kl + 1] = 0.f; d_rgbs[3 * kl + 2] = 0.f; }
+        if (d_nrm) { d_nrm[3 * kl] = rem * gn[0]; d_nrm[3 * kl + 1] = rem * gn[1]; d_nrm[3 * kl + 2] = rem * gn[2]; }
+    }
+    dbeta = ls_warp_sum(dbeta);
+    drlen = ls_warp_sum(drlen);
+    if (lane == 0) {
+        if (d_beta_param) atomicAdd(d_beta_param, dbeta * beta * beta_speed);
+        if (d_ray && rlen > 0.f) {
+            atomicAdd(d_ray + 3 * r, drlen * rx / rlen);
+            atomicAdd(d_ray + 3 * r + 1, drlen * ry / rlen);
+            atomicAdd(d_ray + 3 * r + 2, drlen * rz / rlen);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- unfused hash-grid encoding (tcnn.Encoding) [EXT]
+// one thread per (point, level); u in (nominally) [0,1]^3.
+__global__ void ls_grid_encode_kernel(const ls2fm_field_t f, const float* __restrict__ u, int64_t m,
+                                      float* __restrict__ enc, uint32_t* __restrict__ idx_out) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int L = f.n_levels;
+    if (gid >= m * L) return;
+    const int64_t i = gid / L;
+    const int l = (int)(gid - i * L);
+    const float uu[3] = {u[3 * i], u[3 * i + 1], u[3 * i + 2]};
+    const float scale = f.levels[l].scale;
+    const uint32_t res = f.levels[l].resolution, size = f.levels[l].size, hashed = f.levels[l].hashed, off = f.levels[l].offset;
+    const LsCell c = ls_cell(scale, uu);
+    float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t idx = ls_corner_index(res, size, hashed, c, k);
+        if (idx_out) idx_out[(i * L + l) * 8 + k] = off + idx;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(f.table) + off + idx);
+        const float wgt = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) * ((k & 4) ? c.w[2] : 1.f - c.w[2]);
+        h0 = fmaf(wgt, v.x, h0);
+        h1 = fmaf(wgt, v.y, h1);
+    }
+    if (enc) { enc[i * 2 * L + 2 * l] = h0; enc[i * 2 * L + 2 * l + 1] = h1; }
+}
+
+// backward: d_table += scatter(g_enc), d_u (nullable, written by the level-0 thread after a warp-free accumulation
+// through atomics because the levels of one point are spread over threads)
+__global__ void ls_grid_encode_backward_kernel(const ls2fm_field_t f, const float* __restrict__ u, int64_t m,
+                                               const float* __restrict__ g_enc, float* __restrict__ d_table,
+                                               float* __restrict__ d_u) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int L = f.n_levels;
+    if (gid >= m * L) return;
+    const int64_t i = gid / L;
+    const int l = (int)(gid - i * L);
+    const float uu[3] = {u[3 * i], u[3 * i + 1], u[3 * i + 2]};
+    const float scale = f.levels[l].scale;
+    const uint32_t res = f.levels[l].resolution, size = f.levels[l].size, hashed = f.levels[l].hashed, off = f.levels[l].offset;
+    const LsCell c = ls_cell(scale, uu);
+    const float g0 = g_enc[i * 2 * L + 2 * l], g1 = g_enc[i * 2 * L + 2 * l + 1];
+    float du[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t idx = ls_corner_index(res, size, hashed, c, k);
+        const float f0 = (k & 1) ? c.w[0] : 1.f - c.w[0];
+        const float f1 = (k & 2) ? c.w[1] : 1.f - c.w[1];
+        const float f2 = (k & 4) ? c.w[2] : 1.f - c.w[2];
+        const float wgt = f0 * f1 * f2;
+        if (d_table) atomicAdd(reinterpret_cast<float2*>(d_table) + off + idx, make_float2(wgt * g0, wgt * g1));
+        if (d_u) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(f.table) + off + idx);
+            const float gv = g0 * v.x + g1 * v.y;
+            du[0] += ((k & 1) ? gv : -gv) * f1 * f2;
+            du[1] += ((k & 2) ? gv : -gv) * f0 * f2;
+            du[2] += ((k & 4) ? gv : -gv) * f0 * f1;
+        }
+    }
+    if (d_u) {
+        atomicAdd(d_u + 3 * i, scale * du[0]);
+        atomicAdd(d_u + 3 * i + 1, scale * du[1]);
+        atomicAdd(d_u + 3 * i + 2, scale * du[2]);
+    }
+}

@@ -1,0 +1,347 @@
+"""Operators of the Level-S2fM render hot path on top of ``libls2fm_sm100.so``.
+
+Low-level ``*_raw`` functions are 1:1 with the C ABI (``include/ls2fm.h``); the
+``torch.autograd.Function`` classes give them the autograd behaviour of the reference's
+eager graph (models/SDF.py, models/RadF.py, models/Renderer.py of the reference).
+PyTorch is only the owner of device memory, streams and the autograd tape here.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field as _dc_field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _C
+
+
+# ------------------------------------------------------------------------- specs
+@dataclass
+class GridSpec:
+    """tcnn-style multiresolution hash grid as the reference configures it (models/base.py:124-139)."""
+    n_levels: int = 16
+    n_features: int = 2
+    log2_hashmap_size: int = 19
+    base_resolution: int = 16
+    per_level_scale: float = 1.3819
+    levels: list = _dc_field(default_factory=list)   # filled by resolve()
+    n_entries: int = 0
+
+    def resolve(self, lib: Optional[_C.Lib] = None) -> "GridSpec":
+        lib = lib or _C.get()
+        self.levels, self.n_entries = lib.grid_meta(self.n_levels, self.n_features, self.log2_hashmap_size,
+                                                    self.base_resolution, self.per_level_scale)
+        return self
+
+    @property
+    def n_params(self) -> int:
+        return self.n_entries * self.n_features
+
+    @property
+    def n_output_dims(self) -> int:
+        return self.n_levels * self.n_features
+
+
+@dataclass
+class FieldSpec:
+    """Hash grid + geometry MLP (SDF field or RadF's Geo_enc)."""
+    grid: GridSpec
+    bound_min: Sequence[float]
+    bound_max: Sequence[float]
+    dims: Sequence[int]                 # [3 + 2L, 64, ..., k_geo + 1]
+    rescale: float = 1.0
+    softplus_beta: float = 100.0
+    softplus_threshold: float = 20.0
+    sdf_sign: float = 1.0               # +1 inside, -1 otherwise (models/SDF.py:62-71)
+    scale_mlp: float = 1.0
+
+    @property
+    def n_layers(self) -> int:
+        return len(self.dims) - 1
+
+    @property
+    def dout(self) -> int:
+        return int(self.dims[-1])
+
+    @property
+    def theta_size(self) -> int:
+        return sum(self.dims[l] * self.dims[l + 1] + self.dims[l + 1] for l in range(self.n_layers))
+
+    def c_field(self, lib: _C.Lib, table: torch.Tensor, theta: Optional[torch.Tensor]) -> _C.Field:
+        f = _C.Field()
+        f.table = lib.ptr(table)
+        f.theta = lib.ptr(theta) if theta is not None else None
+        f.n_levels = self.grid.n_levels
+        for i, lv in enumerate(self.grid.levels):
+            f.levels[i] = lv
+        for d in range(3):
+            f.bound_min[d] = float(self.bound_min[d])
+            f.bound_max[d] = float(self.bound_max[d])
+        f.rescale = float(self.rescale)
+        f.n_layers = self.n_layers
+        for i, d in enumerate(self.dims):
+            f.dims[i] = int(d)
+        f.softplus_beta = float(self.softplus_beta)
+        f.softplus_threshold = float(self.softplus_threshold)
+        f.sdf_sign = float(self.sdf_sign)
+        f.scale_mlp = float(self.scale_mlp)
+        return f
+
+
+@dataclass
+class RadSpec:
+    """Radiance decoder input layout (models/Renderer.py:75; models/RadF.py:52-56)."""
+    n_freq: int = 4
+    k_geo: int = 16
+    k_geo2: int = 0
+
+    @property
+    def in_dim(self) -> int:
+        return 3 + 3 + 3 + 6 * self.n_freq + self.k_geo + self.k_geo2
+
+
+def pack_theta(layers: List[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
+    """[(W [out,in], b [out])...] -> flat theta: for l: W_l^T row-major, then b_l (differentiable)."""
+    parts = []
+    for W, b in layers:
+        parts.append(W.t().reshape(-1))
+        parts.append(b.reshape(-1))
+    return torch.cat(parts)
+
+
+def compose_affine(layers: List[Tuple[torch.Tensor, torch.Tensor]]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The reference's radiance decoder applies no hidden activation (models/base.py:230,257), i.e. it is
+    one affine map: W_eff = W_n ... W_1, b_eff likewise (differentiable w.r.t. every layer)."""
+    W, b = layers[0]
+    for Wn, bn in layers[1:]:
+        b = torch.mv(Wn, b) + bn
+        W = Wn @ W
+    return W.contiguous(), b.contiguous()
+
+
+# ------------------------------------------------------------------------- raw calls
+def _points(lib: _C.Lib, xyz=None, center=None, ray=None, t=None, t_offset=0, n_per_ray=None):
+    p = _C.Points()
+    if xyz is not None:
+        p.xyz = lib.ptr(xyz)
+        p.n = xyz.numel() // 3
+        if ray is not None:                      # explicit points that still belong to rays (radiance needs the direction)
+            p.ray = lib.ptr(ray)
+            p.center = lib.ptr(center) if center is not None else None
+            p.n_rays = ray.numel() // 3
+            p.n_per_ray = int(n_per_ray if n_per_ray is not None else (p.n // max(p.n_rays, 1)))
+    else:
+        p.center, p.ray, p.t = lib.ptr(center), lib.ptr(ray), lib.ptr(t)
+        p.n_rays = center.numel() // 3
+        npr = int(n_per_ray if n_per_ray is not None else t.shape[-1] - t_offset)
+        p.n_per_ray = npr
+        p.t_stride = int(t.shape[-1])
+        p.t_offset = int(t_offset)
+        p.n = p.n_rays * npr
+    return p
+
+
+def _rad(lib: _C.Lib, rs: RadSpec, w_eff, b_eff, geo2):
+    r = _C.Radiance()
+    r.w_eff, r.b_eff = lib.ptr(w_eff), lib.ptr(b_eff)
+    r.in_dim, r.n_freq, r.k_geo, r.k_geo2 = rs.in_dim, rs.n_freq, rs.k_geo, rs.k_geo2
+    r.geo2 = lib.ptr(geo2) if geo2 is not None else None
+    return r
+
+
+def field_forward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: Optional[_C.Radiance],
+                      want_y=False, want_sdf=True, want_nrm=False, want_rgb=False):
+    n, dev = int(pts.n), table.device
+    y = torch.empty(n, spec.dout, device=dev) if want_y else None
+    sdf = torch.empty(n, device=dev) if want_sdf else None
+    nrm = torch.empty(n, 3, device=dev) if want_nrm else None
+    rgb = torch.empty(n, 3, device=dev) if want_rgb else None
+    f = spec.c_field(lib, table, theta)
+    lib.check(lib.dll.ls2fm_field_forward(f, pts, rad, lib.ptr(y), lib.ptr(sdf), lib.ptr(nrm), lib.ptr(rgb), lib.stream()))
+    return y, sdf, nrm, rgb
+
+
+def field_backward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: Optional[_C.Radiance],
+                       g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb,
+                       d_table, d_theta, d_w_eff=None, d_b_eff=None, d_geo2=None):
+    f = spec.c_field(lib, table, theta)
+    lib.check(lib.dll.ls2fm_field_backward(
+        f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
+        lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), lib.stream()))
+
+
+def grid_encode_raw(lib, grid: GridSpec, table, u, want_idx=False):
+    m = u.numel() // 3
+    spec = FieldSpec(grid, (0, 0, 0), (1, 1, 1), [3 + 2 * grid.n_levels, 64, 1])
+    f = spec.c_field(lib, table, None)
+    enc = torch.empty(m, grid.n_output_dims, device=u.device)
+    idx = torch.empty(m, grid.n_levels, 8, dtype=torch.int32, device=u.device) if want_idx else None
+    lib.check(lib.dll.ls2fm_grid_encode(f, lib.ptr(u), m, lib.ptr(enc), lib.ptr(idx, torch.int32), lib.stream()))
+    return enc, idx
+
+
+def grid_encode_backward_raw(lib, grid: GridSpec, table, u, g_enc, d_table, d_u=None):
+    m = u.numel() // 3
+    spec = FieldSpec(grid, (0, 0, 0), (1, 1, 1), [3 + 2 * grid.n_levels, 64, 1])
+    f = spec.c_field(lib, table, None)
+    lib.check(lib.dll.ls2fm_grid_encode_backward(f, lib.ptr(u), m, lib.ptr(g_enc), lib.ptr(d_table), lib.ptr(d_u), lib.stream()))
+
+
+def ray_aabb_raw(lib, rays_o, rays_d, center, half_size):
+    m = rays_o.numel() // 3
+    hits = torch.empty(m, 2, device=rays_o.device)
+    cnt = torch.empty(m, dtype=torch.int32, device=rays_o.device)
+    lib.check(lib.dll.ls2fm_ray_aabb(lib.ptr(rays_o), lib.ptr(rays_d), m, _C.f3(center), _C.f3(half_size),
+                                     lib.ptr(hits), lib.ptr(cnt, torch.int32), lib.stream()))
+    return hits, cnt
+
+
+def sample_uniform_raw(lib, center, ray, n_samples, bound_min, bound_max):
+    r = center.numel() // 3
+    t = torch.empty(r, n_samples, device=center.device)
+    hits = torch.empty(r, 2, device=center.device)
+    lib.check(lib.dll.ls2fm_sample_uniform(lib.ptr(center), lib.ptr(ray), r, n_samples, _C.f3(bound_min), _C.f3(bound_max),
+                                           lib.ptr(t), lib.ptr(hits), lib.stream()))
+    return t, hits
+
+
+def composite_forward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bgcolor):
+    r, n = t.shape
+    dev = t.device
+    rgb = torch.empty(r, 3, device=dev) if rgbs is not None else None
+    depth = torch.empty(r, device=dev)
+    normal = torch.empty(r, 3, device=dev) if nrm is not None else None
+    opacity = torch.empty(r, device=dev)
+    lib.check(lib.dll.ls2fm_composite_forward(
+        lib.ptr(ray), lib.ptr(t), lib.ptr(sdf), lib.ptr(rgbs), lib.ptr(nrm), lib.ptr(beta_param), float(beta_speed),
+        _C.f3(bgcolor), r, n, lib.ptr(rgb), lib.ptr(depth), lib.ptr(normal), lib.ptr(opacity), lib.stream()))
+    return rgb, depth, normal, opacity
+
+
+def composite_backward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bgcolor, g_rgb, g_depth, g_normal,
+                           want_d_ray=False):
+    r, n = t.shape
+    dev = t.device
+    d_sdf = torch.empty(r, n, device=dev)
+    d_rgbs = torch.empty(r, n, 3, device=dev) if rgbs is not None else None
+    d_nrm = torch.empty(r, n, 3, device=dev) if nrm is not None else None
+    d_beta = torch.zeros(1, device=dev)
+    d_ray = torch.zeros(r, 3, device=dev) if want_d_ray else None
+    lib.check(lib.dll.ls2fm_composite_backward(
+        lib.ptr(ray), lib.ptr(t), lib.ptr(sdf), lib.ptr(rgbs), lib.ptr(nrm), lib.ptr(beta_param), float(beta_speed),
+        _C.f3(bgcolor), r, n, lib.ptr(g_rgb), lib.ptr(g_depth), lib.ptr(g_normal),
+        lib.ptr(d_sdf), lib.ptr(d_rgbs), lib.ptr(d_nrm), lib.ptr(d_beta), lib.ptr(d_ray), lib.stream()))
+    return d_sdf, d_rgbs, d_nrm, d_beta, d_ray
+
+
+# ------------------------------------------------------------------------- autograd
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
+class FieldEval(torch.autograd.Function):
+    """Fused hash grid + geometry MLP (+ analytic normals, + radiance).
+
+    Differentiable w.r.t. ``table``, ``theta``, ``w_eff``, ``b_eff`` and ``geo2`` -- including the
+    second-order path through the normals (the reference's SDF.gradient uses create_graph=True,
+    models/SDF.py:107-113).  Not differentiable w.r.t. the sample positions (see include/ls2fm.h).
+
+    forward(spec, rad_spec, table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, t_offset, n_per_ray,
+            want_y, want_nrm) -> (sdf [n], y [n,dout] | empty, nrm [n,3] | empty, rgb [n,3] | empty)
+    """
+
+    @staticmethod
+    def forward(ctx, spec, rad_spec, table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, t_offset, n_per_ray,
+                want_y, want_nrm):
+        lib = _C.get()
+        table, theta = table.detach().contiguous(), theta.detach().contiguous()
+        xyz, center, ray, t = _c(xyz), _c(center), _c(ray), _c(t)
+        with_rad = w_eff is not None
+        if with_rad:
+            w_eff, b_eff = w_eff.detach().contiguous(), b_eff.detach().contiguous()
+            geo2 = _c(geo2.detach()) if geo2 is not None else None
+        pts = _points(lib, xyz, center, ray, t, t_offset, n_per_ray)
+        rad = _rad(lib, rad_spec, w_eff, b_eff, geo2) if with_rad else None
+        y, sdf, nrm, rgb = field_forward_raw(lib, spec, table, theta, pts, rad, want_y=want_y, want_sdf=True,
+                                             want_nrm=want_nrm or with_rad, want_rgb=with_rad)
+        ctx.spec, ctx.rad_spec = spec, rad_spec
+        ctx.pt_args = (t_offset, n_per_ray)
+        ctx.with_rad, ctx.want_y, ctx.want_nrm = with_rad, want_y, want_nrm
+        ctx.save_for_backward(table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, nrm if with_rad else None, rgb)
+        empty = table.new_empty(0)
+        outs = (sdf, y if want_y else empty, nrm if (want_nrm or with_rad) else empty, rgb if with_rad else empty)
+        ctx.mark_non_differentiable(*[o for o in outs if o.numel() == 0 and o is empty])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_y, g_nrm, g_rgb):
+        lib = _C.get()
+        table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, s_nrm, s_rgb = ctx.saved_tensors
+        spec, rs = ctx.spec, ctx.rad_spec
+        pts = _points(lib, xyz, center, ray, t, *ctx.pt_args)
+        with_rad = ctx.with_rad and g_rgb is not None
+        rad = _rad(lib, rs, w_eff, b_eff, geo2) if with_rad else None
+        g_y = _c(g_y) if (ctx.want_y and g_y is not None) else None
+        g_nrm = _c(g_nrm) if ((ctx.want_nrm or ctx.with_rad) and g_nrm is not None) else None
+        g_rgb = _c(g_rgb) if with_rad else None
+        g_sdf = _c(g_sdf) if g_sdf is not None else None
+        d_table = torch.zeros_like(table)
+        d_theta = torch.zeros_like(theta)
+        d_w = torch.zeros_like(w_eff) if with_rad else None
+        d_b = torch.zeros_like(b_eff) if with_rad else None
+        d_geo2 = torch.empty_like(geo2) if (with_rad and geo2 is not None) else None
+        field_backward_raw(lib, spec, table, theta, pts, rad, g_y, g_sdf, g_nrm, g_rgb, s_nrm, s_rgb,
+                           d_table, d_theta, d_w, d_b, d_geo2)
+        return (None, None, d_table, d_theta, d_w, d_b, d_geo2, None, None, None, None, None, None, None, None)
+
+
+class Composite(torch.autograd.Function):
+    """Laplace-CDF density + alpha compositing + background fill (models/Renderer.py:33-49,80-107).
+
+    forward(ray [R,3], t [R,N], sdf [R,N], rgbs [R,N,3], nrm [R,N,3], beta_param [1], beta_speed, bgcolor)
+        -> rgb [R,3], depth [R], normal [R,3], opacity [R]
+    """
+
+    @staticmethod
+    def forward(ctx, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bgcolor):
+        lib = _C.get()
+        ray, t, sdf, rgbs, nrm = _c(ray.detach()), _c(t.detach()), _c(sdf.detach()), _c(rgbs.detach()), _c(nrm.detach())
+        beta_param = beta_param.detach().contiguous()
+        rgb, depth, normal, opacity = composite_forward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bgcolor)
+        ctx.save_for_backward(ray, t, sdf, rgbs, nrm, beta_param)
+        ctx.misc = (beta_speed, tuple(bgcolor))
+        ctx.mark_non_differentiable(opacity)
+        return rgb, depth, normal, opacity
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_normal, _g_op):
+        lib = _C.get()
+        ray, t, sdf, rgbs, nrm, beta_param = ctx.saved_tensors
+        beta_speed, bg = ctx.misc
+        want_ray = ctx.needs_input_grad[0]
+        d_sdf, d_rgbs, d_nrm, d_beta, d_ray = composite_backward_raw(
+            lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bg, _c(g_rgb), _c(g_depth), _c(g_normal), want_ray)
+        return d_ray, None, d_sdf, d_rgbs, d_nrm, d_beta.view_as(beta_param), None, None
+
+
+class GridEncode(torch.autograd.Function):
+    """``tcnn.Encoding`` replacement (models/base.py:17,37): u [M,3] -> [M, L*F]; grads to the table and to u."""
+
+    @staticmethod
+    def forward(ctx, grid, table, u):
+        lib = _C.get()
+        table, u = table.detach().contiguous(), u.detach().contiguous()
+        enc, _ = grid_encode_raw(lib, grid, table, u)
+        ctx.grid = grid
+        ctx.save_for_backward(table, u)
+        return enc
+
+    @staticmethod
+    def backward(ctx, g_enc):
+        lib = _C.get()
+        table, u = ctx.saved_tensors
+        d_table = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
+        d_u = torch.zeros_like(u) if ctx.needs_input_grad[2] else None
+        grid_encode_backward_raw(lib, ctx.grid, table, u, g_enc.contiguous(), d_table, d_u)
+        return None, d_table, d_u
