@@ -71,6 +71,7 @@ static int ls_check_field(const ls2fm_field_t* f) {
 static int ls_check_points(const ls2fm_points_t* p) {
     if (!p) return ls_fail("points is NULL");
     if (p->n < 0) return ls_fail("points.n < 0");
+    if (p->n == 0) return 0;
     if (!p->xyz) {
         if (!p->center || !p->ray || !p->t) return ls_fail("ray mode needs center, ray and t");
         if (p->n_per_ray <= 0 || p->n_rays < 0) return ls_fail("ray mode needs n_per_ray > 0");
@@ -188,9 +189,9 @@ int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64
 int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, float* out_y,
                         float* out_sdf, float* out_nrm, float* out_rgb, void* stream) {
     if (ls_check_field(field) || ls_check_points(pts)) return 1;
+    if (pts->n == 0) return 0;
     if (rad && ls_check_rad(rad, field, pts)) return 1;
     if (out_rgb && !rad) return ls_fail("field_forward: out_rgb needs the radiance block");
-    if (pts->n == 0) return 0;
     LsFieldArgs a;
     ls_fill_args(a, field, pts, rad);
     a.out_y = out_y; a.out_sdf = out_sdf; a.out_nrm = out_nrm; a.out_rgb = out_rgb;
@@ -215,6 +216,7 @@ int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, 
                          const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
                          void* stream) {
     if (ls_check_field(field) || ls_check_points(pts)) return 1;
+    if (pts->n == 0) return 0;
     if (rad && ls_check_rad(rad, field, pts)) return 1;
     if (rad && g_rgb && (!saved_nrm || !saved_rgb)) return ls_fail("field_backward: saved_nrm / saved_rgb required with radiance");
     if (!rad && (g_rgb || d_w_eff || d_b_eff || d_geo2)) return ls_fail("field_backward: radiance gradients need the radiance block");

@@ -1,0 +1,80 @@
+"""Per-ray SDF volume renderer of Level-S2fM on the fused sm_100a kernels (reference: models/Renderer.py).
+
+``Renderer.forward(opt, center, ray, SDF_Field, Rad_Field)`` returns the reference's dict
+(rgb, sdfs_volume, normals, depth_mlp, normal_mlp).  Launches per call: depth sampler, [second field when
+dual_field], fused field kernel (hash + MLP + normals + radiance), compositing.  Backward: compositing backward,
+fused field backward.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _C, ops
+
+
+class Renderer:
+    def __init__(self, opt):
+        self.opt = opt
+        dev = opt.device
+        self.bound_max = torch.tensor(np.array(opt.data.bound_max), dtype=torch.float32, device=dev)[None, None, :]
+        self.bound_min = torch.tensor(np.array(opt.data.bound_min), dtype=torch.float32, device=dev)[None, None, :]
+        self.center = (self.bound_max + self.bound_min) / 2
+        self.half_size = (self.bound_max - self.bound_min) / 2
+        scene = opt.data[f"{opt.data.scene}"] if f"{opt.data.scene}" in opt.data else None
+        bgcolor = getattr(scene, "bgcolor", None) if scene is not None else None
+        if bgcolor is None:
+            bgcolor = opt.data.bgcolor
+        self.bgcolor = torch.tensor(np.array(bgcolor), dtype=torch.float32, device=dev)
+        self._bg = tuple(float(x) for x in np.array(bgcolor).reshape(-1)[:3])
+
+    # ------------------------------------------------------------------ samplers
+    def sample_depth(self, opt, min_d=None, max_d=None):
+        """(i + 0.5) / N * (max_d - min_d) + min_d, [..., N, 1] (models/Renderer.py:118-127)."""
+        n = opt.SDF.VolSDF.sample_intvs
+        i = 0.5 + torch.arange(n, device=min_d.device)[None, None, :, None].float()
+        return i / n * (max_d[..., None, :] - min_d[..., None, :]) + min_d[..., None, :]
+
+    def volsdf_sampling(self, opt, center, ray, SDF_Field, det=True):
+        """Depth samples [B,R,N] (returned three times like the reference's default branch)."""
+        B, R = center.shape[:2]
+        c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
+        v = opt.SDF.VolSDF
+        if v.volsdf_sampling == True:   # noqa: E712
+            from .. import sampler
+            t, beta_plus, iters = sampler.error_bounded(self, opt, c2, r2, SDF_Field)
+            return t.view(B, R, -1), beta_plus.view(B, R), iters.view(B, R)
+        t, _ = ops.sample_uniform_raw(_C.get(), c2, r2, int(v.sample_intvs), [float(x) for x in opt.data.bound_min],
+                                      [float(x) for x in opt.data.bound_max])
+        t = t.view(B, R, -1)
+        return t, t, t
+
+    # ------------------------------------------------------------------ the hot path
+    def forward(self, opt, center, ray, SDF_Field, Rad_Field):
+        B, R = center.shape[:2]
+        t, _, _ = self.volsdf_sampling(opt, center, ray, SDF_Field=SDF_Field)
+        N = t.shape[-1]
+        c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
+        t2 = t.reshape(B * R, N).contiguous()
+        geo2 = None
+        if Rad_Field.dual_field:
+            _, geo2, _, _ = ops.FieldEval.apply(Rad_Field.field_spec(), None, Rad_Field.embed_fn.embedder_obj.params,
+                                                Rad_Field.Geo_enc.theta(), None, None, None, None, c2, r2, t2, 0, None,
+                                                True, False)
+        w_eff, b_eff = Rad_Field.Rad_dec.effective_affine()
+        sdf, _, nrm, rgbs = ops.FieldEval.apply(SDF_Field.field_spec(), Rad_Field.rad_spec(), SDF_Field.table(),
+                                                SDF_Field.SDF_MLP.theta(), w_eff, b_eff, geo2, None, c2, r2, t2, 0, None,
+                                                False, True)
+        ray_in = ray.reshape(-1, 3).float() if ray.requires_grad else r2
+        rgb, depth, normal, _ = ops.Composite.apply(ray_in, t2, sdf.view(B * R, N), rgbs.view(B * R, N, 3),
+                                                    nrm.view(B * R, N, 3), SDF_Field.beta, float(SDF_Field.beta_speed),
+                                                    self._bg)
+        return {"rgb": rgb.view(B, R, 3), "sdfs_volume": sdf.view(B, R, N, 1), "normals": nrm.view(B, R, N, 3),
+                "depth_mlp": depth.view(B, R, 1), "normal_mlp": normal.view(B, R, 3)}
+
+    render_rays = forward    # north-star alias
+
+    # ------------------------------------------------------------------ API-compatible pieces
+    def sdf_to_sigma(self, sdf, alpha, beta):
+        e = 0.5 * torch.exp(-torch.abs(sdf) / beta)
+        return alpha * torch.where(sdf >= 0, e, 1 - e)

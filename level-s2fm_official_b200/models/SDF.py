@@ -1,0 +1,155 @@
+"""SDF field of Level-S2fM on the fused sm_100a kernels (reference: models/SDF.py).
+
+Same constructor, attributes, method names and state-dict keys as the reference class
+(``beta``, ``embed_fn.embedder_obj.params``, ``SDF_MLP.mlp.{i}.{bias,weight_g,weight_v}``), so the reference's
+``pipelines/`` can use it unchanged.  Every evaluation is ONE launch of the fused hash-grid + MLP (+ normals)
+kernel; autograd sees a single node whose backward is the fused backward kernel (second-order path included).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .base import Geometry, get_Embedder, get_layer_dims
+
+
+class SDF(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        dev = opt.device
+        self.bound_max = torch.tensor(np.array(opt.data.bound_max), dtype=torch.float32, device=dev)[None, None, :]
+        self.bound_min = torch.tensor(np.array(opt.data.bound_min), dtype=torch.float32, device=dev)[None, None, :]
+        self.center = (self.bound_max + self.bound_min) / 2
+        self.half_size = (self.bound_max - self.bound_min) / 2
+        v = opt.SDF.VolSDF
+        self.rescale = v.rescale
+        self.beta_speed = v.beta_speed
+        beta_init = np.log(v.beta_init) / self.beta_speed
+        self.beta = nn.Parameter(torch.tensor([beta_init], dtype=torch.float32, device=dev))
+        self.sdf_threshold = float(v.sdf_threshold)
+        self.iters_max = int(v.iters_max_st)
+        self.scale_mlp = opt.SDF.NN_Init.scale_mlp
+        self.define_network(opt)
+
+    def define_network(self, opt):
+        self.embed_fn = get_Embedder(opt=opt, input_dim=3)
+        self.SDF_MLP = Geometry(opt=opt, input_dim=self.embed_fn.out_dim, skip=opt.SDF.arch.skip,
+                                tf_init=opt.SDF.NN_Init.tf_init, layers=get_layer_dims(opt.SDF.arch.layers))
+
+    # ------------------------------------------------------------------ kernel plumbing
+    def field_spec(self) -> ops.FieldSpec:
+        inside = self.opt.data.inside == True   # noqa: E712  (the reference compares with == True)
+        return ops.FieldSpec(self.embed_fn.embedder_obj.grid, [float(x) for x in self.opt.data.bound_min],
+                             [float(x) for x in self.opt.data.bound_max], self.SDF_MLP.dims(), float(self.rescale),
+                             100.0, 20.0, 1.0 if inside else -1.0, float(self.scale_mlp))
+
+    def table(self):
+        return self.embed_fn.embedder_obj.params
+
+    def _eval(self, xyz, want_y=False, want_nrm=False):
+        shp = xyz.shape[:-1]
+        flat = xyz.detach().reshape(-1, 3).float()
+        sdf, y, nrm, _ = ops.FieldEval.apply(self.field_spec(), None, self.table(), self.SDF_MLP.theta(), None, None, None,
+                                             flat, None, None, None, 0, None, want_y, want_nrm)
+        sdf = sdf.view(*shp, 1)
+        if self.opt.data.inside == True and getattr(self.opt.data, "bg_sdf", False) == True:  # noqa: E712
+            sdf = torch.min(sdf, self.opt.data.bg_rad - xyz.detach().norm(dim=-1, keepdim=True))
+        return sdf, (y.view(*shp, -1) if want_y else None), (nrm.view(*shp, 3) if want_nrm else None)
+
+    # ------------------------------------------------------------------ reference surface
+    def infer_sdf(self, xyz, mode="ret_sdf"):
+        sdf, feat, _ = self._eval(xyz, want_y=mode != "ret_sdf")
+        if mode == "ret_sdf":
+            return sdf
+        if mode == "ret_feat":
+            return feat
+        return sdf, feat
+
+    forward = infer_sdf      # north-star alias (the reference class defines no forward; its sampler calls one)
+
+    def forward_ab(self):
+        beta = torch.exp(self.beta * self.beta_speed)
+        return 1.0 / beta, beta
+
+    def sdf_to_sigma(self, sdf, alpha, beta):
+        e = 0.5 * torch.exp(-torch.abs(sdf) / beta)
+        return alpha * torch.where(sdf >= 0, e, 1 - e)
+
+    def density(self, opt, xyzs):
+        alpha, beta = self.forward_ab()
+        return self.sdf_to_sigma(self.infer_sdf(xyzs), alpha, beta)
+
+    def gradient(self, p):
+        """d sdf / d p by the kernel's analytic reverse sweep.  Like the reference (create_graph=True) the result
+        stays differentiable w.r.t. the field parameters."""
+        p.requires_grad_(True)
+        return self._eval(p, want_nrm=True)[2]
+
+    def sdf_and_gradient(self, p):
+        sdf, _, nrm = self._eval(p, want_nrm=True)
+        return sdf, nrm
+
+    def get_surface_pts(self, pts):
+        """One Newton projection onto the zero level set (models/SDF.py:95-100); one fused launch."""
+        sdf, normals = self.sdf_and_gradient(pts)
+        normals_value = torch.norm(normals, dim=-1, keepdim=True)
+        surf_pts = pts - normals / normals_value.detach() * sdf
+        return surf_pts, normals_value
+
+    def sphere_tracing(self, ray0, ray_direction, model=None, c=None, tau=0.5, n_steps=(128, 129), n_secant_steps=8,
+                       depth_range=(0.0, 2.4), max_points=3500000, rad=1.0, iter=0):
+        """Bidirectional sphere tracing (models/SDF.py:116-226).  Returns (d_pred [B,M] differentiable w.r.t. the
+        field parameters, sdf_last [B*M], sampled_pts [1,*,3] (random eikonal points), finish_mask [B*M,1])."""
+        lib_o, lib_d = ray0.detach().reshape(-1, 3).float().contiguous(), ray_direction.detach().reshape(-1, 3).float().contiguous()
+        from .. import _C
+        hits, _ = ops.ray_aabb_raw(_C.get(), lib_o, lib_d, self.center.view(3).tolist(), self.half_size.view(3).tolist())
+        t_near, t_far = hits[:, 0], hits[:, 1]
+        thr = self.sdf_threshold
+        with torch.no_grad():
+            acc_s, acc_e = t_near.clone(), t_far.clone()
+            p_s = lib_o + acc_s[:, None] * lib_d
+            p_e = lib_o + acc_e[:, None] * lib_d
+            both = self.infer_sdf(torch.stack([p_s, p_e]))[..., 0]
+            s_s, s_e = both[0].clone(), both[1].clone()
+            un_s = un_e = None
+            track = []
+            iters = 0
+            while True:
+                s_s = torch.where(s_s.abs() <= thr, torch.zeros_like(s_s), s_s)
+                s_e = torch.where(s_e.abs() <= thr, torch.zeros_like(s_e), s_e)
+                if un_s is None:
+                    un_s, un_e = s_s.abs() > thr, s_e.abs() > thr
+                else:
+                    un_s, un_e = un_s & (s_s.abs() > thr), un_e & (s_e.abs() > thr)
+                if iters == self.iters_max or not bool(un_s.any()):
+                    break
+                iters += 1
+                acc_s = torch.minimum(acc_s + s_s, t_far)
+                acc_e = torch.minimum(acc_e + s_e, t_far)
+                track.append(p_s)
+                p_s = lib_o + acc_s[:, None] * lib_d
+                p_e = lib_o + acc_e[:, None] * lib_d
+                both = self.infer_sdf(torch.stack([p_s, p_e]))[..., 0]
+                s_s = torch.where(un_s, both[0], s_s)
+                s_e = torch.where(un_e, both[1], s_e)
+                un_s, un_e = un_s & (acc_s < acc_e), un_e & (acc_s < acc_e)
+            if not track:
+                track = [p_s]
+            pts_tracks = torch.stack(track, dim=1)                       # [M,K,3]
+        sdf_tracks = self.infer_sdf(pts_tracks)                          # [M,K,1], with grad
+        d_pred = sdf_tracks.sum(dim=-2).view(*ray0.shape[:-1]) + t_near.view(*ray0.shape[:-1])
+        d_pred = torch.minimum(d_pred, t_far.view(*d_pred.shape))
+        thr2 = float(self.opt.data.bound_max[0] - self.opt.data.bound_min[0]) / 10 / self.opt.Res
+        finish_mask = sdf_tracks[:, -1, :].abs() < thr2
+        # random points for the eikonal term (models/SDF.py:216-224)
+        tf_v, tn_v = t_far.view(*d_pred.shape), t_near.view(*d_pred.shape)
+        factor_rand = torch.rand_like(d_pred)
+        d_up = torch.minimum(1.5 * acc_e.view(*d_pred.shape), tf_v)
+        d_sample = (1 - factor_rand) * d_up + factor_rand * tn_v
+        sampled_pts = ray0.detach() + d_sample[..., None].detach() * ray_direction.detach()
+        pick = torch.randperm(pts_tracks.shape[0], device=pts_tracks.device)[:4096]
+        sampled_pts = torch.cat([pts_tracks[pick].view(1, -1, 3), sampled_pts.view(1, -1, 3)], dim=1)
+        return d_pred, sdf_tracks[:, -1, 0], sampled_pts, finish_mask

@@ -120,6 +120,54 @@ def compose_affine(layers: List[Tuple[torch.Tensor, torch.Tensor]]) -> Tuple[tor
     return W.contiguous(), b.contiguous()
 
 
+# ------------------------------------------------------------------------- launch log
+class KernelLog:
+    """Counts the launches of our kernels and, when ``timing`` is on, brackets each launch with CUDA events on the
+    launching stream (used by bench.py for ``gpu_launches`` and the roofline of the dominant kernel)."""
+
+    def __init__(self):
+        self.counts = {}
+        self.timing = False
+        self.events = []        # (name, start, end)
+
+    def reset(self):
+        self.counts = {}
+        self.events = []
+
+    def total(self):
+        return sum(self.counts.values())
+
+    def begin(self, name):
+        self.counts[name] = self.counts.get(name, 0) + 1
+        if self.timing:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            return ev
+        return None
+
+    def end(self, name, start):
+        if start is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.events.append((name, start, ev))
+
+    def durations_ms(self):
+        """name -> list of per-launch durations (call after torch.cuda.synchronize())."""
+        out = {}
+        for name, a, b in self.events:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+
+KLOG = KernelLog()
+
+
+def _call(lib, name, fn, *args):
+    ev = KLOG.begin(name)
+    lib.check(fn(*args))
+    KLOG.end(name, ev)
+
+
 # ------------------------------------------------------------------------- raw calls
 def _points(lib: _C.Lib, xyz=None, center=None, ray=None, t=None, t_offset=0, n_per_ray=None):
     p = _C.Points()
@@ -158,7 +206,7 @@ def field_forward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: O
     nrm = torch.empty(n, 3, device=dev) if want_nrm else None
     rgb = torch.empty(n, 3, device=dev) if want_rgb else None
     f = spec.c_field(lib, table, theta)
-    lib.check(lib.dll.ls2fm_field_forward(f, pts, rad, lib.ptr(y), lib.ptr(sdf), lib.ptr(nrm), lib.ptr(rgb), lib.stream()))
+    _call(lib, "field_forward", lib.dll.ls2fm_field_forward, f, pts, rad, lib.ptr(y), lib.ptr(sdf), lib.ptr(nrm), lib.ptr(rgb), lib.stream())
     return y, sdf, nrm, rgb
 
 
@@ -166,9 +214,8 @@ def field_backward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: 
                        g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb,
                        d_table, d_theta, d_w_eff=None, d_b_eff=None, d_geo2=None):
     f = spec.c_field(lib, table, theta)
-    lib.check(lib.dll.ls2fm_field_backward(
-        f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
-        lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), lib.stream()))
+    _call(lib, "field_backward", lib.dll.ls2fm_field_backward, f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
+        lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), lib.stream())
 
 
 def grid_encode_raw(lib, grid: GridSpec, table, u, want_idx=False):
@@ -177,7 +224,7 @@ def grid_encode_raw(lib, grid: GridSpec, table, u, want_idx=False):
     f = spec.c_field(lib, table, None)
     enc = torch.empty(m, grid.n_output_dims, device=u.device)
     idx = torch.empty(m, grid.n_levels, 8, dtype=torch.int32, device=u.device) if want_idx else None
-    lib.check(lib.dll.ls2fm_grid_encode(f, lib.ptr(u), m, lib.ptr(enc), lib.ptr(idx, torch.int32), lib.stream()))
+    _call(lib, "grid_encode", lib.dll.ls2fm_grid_encode, f, lib.ptr(u), m, lib.ptr(enc), lib.ptr(idx, torch.int32), lib.stream())
     return enc, idx
 
 
@@ -185,15 +232,15 @@ def grid_encode_backward_raw(lib, grid: GridSpec, table, u, g_enc, d_table, d_u=
     m = u.numel() // 3
     spec = FieldSpec(grid, (0, 0, 0), (1, 1, 1), [3 + 2 * grid.n_levels, 64, 1])
     f = spec.c_field(lib, table, None)
-    lib.check(lib.dll.ls2fm_grid_encode_backward(f, lib.ptr(u), m, lib.ptr(g_enc), lib.ptr(d_table), lib.ptr(d_u), lib.stream()))
+    _call(lib, "grid_encode_backward", lib.dll.ls2fm_grid_encode_backward, f, lib.ptr(u), m, lib.ptr(g_enc), lib.ptr(d_table), lib.ptr(d_u), lib.stream())
 
 
 def ray_aabb_raw(lib, rays_o, rays_d, center, half_size):
     m = rays_o.numel() // 3
     hits = torch.empty(m, 2, device=rays_o.device)
     cnt = torch.empty(m, dtype=torch.int32, device=rays_o.device)
-    lib.check(lib.dll.ls2fm_ray_aabb(lib.ptr(rays_o), lib.ptr(rays_d), m, _C.f3(center), _C.f3(half_size),
-                                     lib.ptr(hits), lib.ptr(cnt, torch.int32), lib.stream()))
+    _call(lib, "ray_aabb", lib.dll.ls2fm_ray_aabb, lib.ptr(rays_o), lib.ptr(rays_d), m, _C.f3(center), _C.f3(half_size),
+                                     lib.ptr(hits), lib.ptr(cnt, torch.int32), lib.stream())
     return hits, cnt
 
 
@@ -201,8 +248,8 @@ def sample_uniform_raw(lib, center, ray, n_samples, bound_min, bound_max):
     r = center.numel() // 3
     t = torch.empty(r, n_samples, device=center.device)
     hits = torch.empty(r, 2, device=center.device)
-    lib.check(lib.dll.ls2fm_sample_uniform(lib.ptr(center), lib.ptr(ray), r, n_samples, _C.f3(bound_min), _C.f3(bound_max),
-                                           lib.ptr(t), lib.ptr(hits), lib.stream()))
+    _call(lib, "sample_uniform", lib.dll.ls2fm_sample_uniform, lib.ptr(center), lib.ptr(ray), r, n_samples, _C.f3(bound_min), _C.f3(bound_max),
+                                           lib.ptr(t), lib.ptr(hits), lib.stream())
     return t, hits
 
 
@@ -213,9 +260,8 @@ def composite_forward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, b
     depth = torch.empty(r, device=dev)
     normal = torch.empty(r, 3, device=dev) if nrm is not None else None
     opacity = torch.empty(r, device=dev)
-    lib.check(lib.dll.ls2fm_composite_forward(
-        lib.ptr(ray), lib.ptr(t), lib.ptr(sdf), lib.ptr(rgbs), lib.ptr(nrm), lib.ptr(beta_param), float(beta_speed),
-        _C.f3(bgcolor), r, n, lib.ptr(rgb), lib.ptr(depth), lib.ptr(normal), lib.ptr(opacity), lib.stream()))
+    _call(lib, "composite_forward", lib.dll.ls2fm_composite_forward, lib.ptr(ray), lib.ptr(t), lib.ptr(sdf), lib.ptr(rgbs), lib.ptr(nrm), lib.ptr(beta_param), float(beta_speed),
+        _C.f3(bgcolor), r, n, lib.ptr(rgb), lib.ptr(depth), lib.ptr(normal), lib.ptr(opacity), lib.stream())
     return rgb, depth, normal, opacity
 
 
@@ -228,10 +274,9 @@ def composite_backward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, 
     d_nrm = torch.empty(r, n, 3, device=dev) if nrm is not None else None
     d_beta = torch.zeros(1, device=dev)
     d_ray = torch.zeros(r, 3, device=dev) if want_d_ray else None
-    lib.check(lib.dll.ls2fm_composite_backward(
-        lib.ptr(ray), lib.ptr(t), lib.ptr(sdf), lib.ptr(rgbs), lib.ptr(nrm), lib.ptr(beta_param), float(beta_speed),
+    _call(lib, "composite_backward", lib.dll.ls2fm_composite_backward, lib.ptr(ray), lib.ptr(t), lib.ptr(sdf), lib.ptr(rgbs), lib.ptr(nrm), lib.ptr(beta_param), float(beta_speed),
         _C.f3(bgcolor), r, n, lib.ptr(g_rgb), lib.ptr(g_depth), lib.ptr(g_normal),
-        lib.ptr(d_sdf), lib.ptr(d_rgbs), lib.ptr(d_nrm), lib.ptr(d_beta), lib.ptr(d_ray), lib.stream()))
+        lib.ptr(d_sdf), lib.ptr(d_rgbs), lib.ptr(d_nrm), lib.ptr(d_beta), lib.ptr(d_ray), lib.stream())
     return d_sdf, d_rgbs, d_nrm, d_beta, d_ray
 
 
@@ -269,10 +314,11 @@ class FieldEval(torch.autograd.Function):
         ctx.pt_args = (t_offset, n_per_ray)
         ctx.with_rad, ctx.want_y, ctx.want_nrm = with_rad, want_y, want_nrm
         ctx.save_for_backward(table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, nrm if with_rad else None, rgb)
-        empty = table.new_empty(0)
-        outs = (sdf, y if want_y else empty, nrm if (want_nrm or with_rad) else empty, rgb if with_rad else empty)
-        ctx.mark_non_differentiable(*[o for o in outs if o.numel() == 0 and o is empty])
-        return outs
+        out_y = y if want_y else table.new_empty(0)
+        out_nrm = nrm if (want_nrm or with_rad) else table.new_empty(0)
+        out_rgb = rgb if with_rad else table.new_empty(0)
+        ctx.mark_non_differentiable(*[o for o in (out_y, out_nrm, out_rgb) if o.numel() == 0])
+        return sdf, out_y, out_nrm, out_rgb
 
     @staticmethod
     def backward(ctx, g_sdf, g_y, g_nrm, g_rgb):

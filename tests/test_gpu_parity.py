@@ -1,0 +1,146 @@
+"""Parity tests proper: the sm_100a library through the C ABI / drop-in python surface vs the CPU oracle and the
+golden fixtures the reference's own python produced.  Tolerance: 1e-4 relative in fp32 (BASELINE.json north_star),
+hash-table indices bit-exact."""
+import pytest
+import torch
+
+from oracle import hashgrid, port
+
+from . import common
+from . import golden_checks as gc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def product_lib():
+    from levels2fm_b200 import _C
+    lib = _C.get()
+    assert "libls2fm_sm100.so" in lib.path
+    return lib
+
+
+def test_hash_indices_bit_exact(product_lib):
+    from levels2fm_b200 import ops
+    for half, L in ((1.0, 16), (5.0, 16), (1.0, 4)):
+        cfg = port.SceneCfg(bound_min=(-half,) * 3, bound_max=(half,) * 3, n_levels=L)
+        meta = cfg.grid()
+        grid = ops.GridSpec(L, 2, 19, 16, cfg.per_level_scale).resolve()
+        g = torch.Generator().manual_seed(0)
+        u = torch.rand(100000, 3, generator=g)
+        u[:10000] = u[:10000] * 3 - 1
+        u[10000:20000] = torch.round(u[10000:20000] * 64) / 64
+        table = torch.randn(meta.n_params, generator=g)
+        enc, idx = ops.grid_encode_raw(product_lib, grid, table.to(DEV), u.to(DEV), want_idx=True)
+        idx = idx.cpu().to(torch.int64) & 0xFFFFFFFF
+        for l, lv in enumerate(meta.levels):
+            ref_idx, _ = hashgrid.corner_indices(u, lv)
+            assert torch.equal(idx[:, l, :], ref_idx + lv.offset), f"half {half} level {l}"
+        ref = hashgrid.encode(u[:20000], table, meta)
+        assert (enc[:20000].cpu() - ref).abs().max() <= 1e-5 * ref.abs().max()
+
+
+def test_ray_aabb_and_uniform_samples_bit_exact(product_lib):
+    from levels2fm_b200 import ops
+    cfg = port.SceneCfg(sample_intvs=128)
+    center, ray = common.make_rays(2, 4096, 1.0)
+    ray[0, :7] = torch.tensor([0.0, 1.0, 0.0])          # parallel to two slabs: inf arithmetic in the slab test
+    center[0, 7:16] += 10.0                              # misses
+    tn, tf = port.ray_aabb(center, ray, cfg)
+    t_ref = port.sample_depth(tn, tf, 128)
+    c2, r2 = center.reshape(-1, 3).to(DEV), ray.reshape(-1, 3).to(DEV)
+    t, hits = ops.sample_uniform_raw(product_lib, c2, r2, 128, cfg.bound_min, cfg.bound_max)
+    assert torch.equal(hits[:, 0].cpu(), tn.reshape(-1)) and torch.equal(hits[:, 1].cpu(), tf.reshape(-1))
+    assert torch.equal(t.cpu(), t_ref.reshape(-1, 128))
+    hits2, cnt = ops.ray_aabb_raw(product_lib, c2, r2, [0, 0, 0], [1, 1, 1])
+    assert torch.equal(hits2, hits) and torch.equal(cnt.cpu().bool(), (tf.reshape(-1) > 0))
+
+
+@pytest.mark.parametrize("dataset,n_levels,layers,n_samples,n_rays,dual", [
+    ("DTU", 4, (None, 64, 16), 64, 128, False),                 # BASELINE config 1 shape
+    ("DTU", 16, (None, 64, 64, 64, 16), 128, 64, False),        # config 2 networks, uniform samples
+    ("ETH3D", 16, (None, 64, 16), 128, 96, False),              # config 3 bounds (inside: false)
+    ("bmvs", 16, (None, 64, 16), 48, 40, True),                 # dual_field
+    ("DTU", 16, (None, 64, 64, 16), 33, 7, False),              # ragged: samples not a multiple of the warp tile
+])
+def test_render_forward_backward_matches_oracle(dataset, n_levels, layers, n_samples, n_rays, dual):
+    opt = common.make_opt(dataset, DEV, n_levels, layers, n_samples, dual)
+    outs, grads = common.render_parity_case(opt, n_levels, 2, n_rays, device=DEV)
+    for k, (a, b) in outs.items():
+        assert common.rel_err(a, b) < 1e-4, (k, common.rel_err(a, b))
+    for k, (a, b) in grads.items():
+        assert common.cosine(a, b) > 1 - 1e-6, (k, common.cosine(a, b))
+        assert common.rel_err(a, b) < 2e-3, (k, common.rel_err(a, b))
+
+
+def test_golden_c1_render():
+    gold = gc.load("c1_render.npz")
+    out, grads, loss = gc.run_c1_product(gold, DEV)
+    gc.check_c1(out, grads, loss, gold)
+
+
+def test_golden_sphere_tracing_and_surface_points():
+    gold = gc.load("st_dtu.npz")
+    gc.check_st(*gc.run_st_product(gold, DEV), gold)
+
+
+def test_ragged_tiny_and_empty_inputs():
+    opt = common.make_opt("DTU", DEV, 4, (None, 64, 16), 16)
+    cfg = common.cfg_of(opt, 4)
+    sdf_sd, _ = port.random_state(cfg, seed=2, table_std=0.2)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    g = torch.Generator().manual_seed(0)
+    for n in (1, 7, 65, 130, 1000):
+        x = torch.rand(n, 3, generator=g) * 1.6 - 0.8
+        s, f = sdf.infer_sdf(x.to(DEV), mode="ret_all")
+        rs, rf = port.infer_sdf(x, sdf_sd, cfg, "ret_all")
+        assert common.rel_err(s.cpu(), rs) < 1e-5 and common.rel_err(f.cpu(), rf) < 1e-5
+        n_ours = sdf.gradient(x.clone().to(DEV))
+        n_ref = port.sdf_gradient(x.clone(), sdf_sd, cfg)
+        assert common.rel_err(n_ours.cpu(), n_ref.detach()) < 1e-5
+    assert sdf.infer_sdf(torch.zeros(0, 3, device=DEV)).shape == (0, 1)
+    assert sdf.infer_sdf(torch.zeros(2, 5, 3, device=DEV)).shape == (2, 5, 1)
+
+
+def test_full_size_properties():
+    """BASELINE sizes (4096 rays x 128 samples, L=16, 3x64 + 2x64): size-independent properties of the path."""
+    opt = common.make_opt("DTU", DEV, 16, (None, 64, 64, 64, 16), 128)
+    cfg = common.cfg_of(opt, 16)
+    sdf_sd, rad_sd = port.random_state(cfg, seed=3, table_std=0.05, generic_weights=False, hash_weight_std=0.05)
+    sdf, rad, ren = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    rad.load_state_dict(rad_sd)
+    center, ray = common.make_rays(2, 2048, 1.0)
+    center, ray = center.to(DEV), ray.to(DEV)
+    out = ren.forward(opt, center, ray, sdf, rad)
+    assert all(torch.isfinite(v).all() for v in out.values())
+    assert out["rgb"].min() >= 0 and out["rgb"].max() <= 1 + 1e-6             # convex combination of sigmoids and bg
+    # linearity / determinism: rendering the rays in two halves gives the same per-ray values
+    o2 = ren.forward(opt, center[:, :1024], ray[:, :1024], sdf, rad)
+    assert torch.equal(o2["rgb"], out["rgb"][:, :1024]) and torch.equal(o2["normals"], out["normals"][:, :1024])
+    # a spot-check subset against the oracle at full size
+    sub = slice(0, 16)
+    ref = port.render_forward(center[:1, sub].cpu(), ray[:1, sub].cpu(), sdf_sd, rad_sd, cfg)
+    for k in ("rgb", "depth_mlp", "normal_mlp", "sdfs_volume", "normals"):
+        assert common.rel_err(out[k][:1, sub].cpu(), ref[k].detach()) < 1e-4, k
+    # gradient of a sum over rays == sum of gradients of the two halves (scatter/accumulate is additive)
+    gt = torch.rand(2, 2048, 3, device=DEV)
+
+    def grads_of(sl):
+        for p in list(sdf.parameters()) + list(rad.parameters()):
+            p.grad = None
+        o = ren.forward(opt, center[:, sl], ray[:, sl], sdf, rad)
+        ((o["rgb"] - gt[:, sl]).abs().sum() + (o["normals"].norm(dim=-1) - 1).abs().sum() * 1e-2).backward()
+        return [p.grad.clone() for p in list(sdf.parameters()) + list(rad.parameters())]
+    ga, gb, gall = grads_of(slice(0, 1024)), grads_of(slice(1024, 2048)), grads_of(slice(0, 2048))
+    for a, b, c in zip(ga, gb, gall):
+        assert common.cosine(a + b, c) > 1 - 1e-6
+
+
+def test_errors_are_raised(product_lib):
+    from levels2fm_b200 import ops
+    with pytest.raises(RuntimeError, match="n_samples"):
+        ops.composite_forward_raw(product_lib, torch.ones(2, 3, device=DEV), torch.ones(2, 1, device=DEV),
+                                  torch.ones(2, 1, device=DEV), None, None, torch.zeros(1, device=DEV), 1.0, (0, 0, 0))

@@ -1,0 +1,86 @@
+"""Kernel ARITHMETIC checked on the CPU: the very same csrc/*.cu* sources compiled by g++ against the SIMT emulator
+(tests/hostsim/simt.h) and driven through the same C ABI + python layer as on the GPU.  This is test infrastructure
+for a container without a GPU; the product library is the nvcc build and the -m gpu tests are the parity tests proper."""
+import pytest
+import torch
+
+from oracle import port
+
+from . import common
+from . import golden_checks as gc
+
+
+@pytest.fixture(scope="module", autouse=True)
+def hostsim_lib():
+    from levels2fm_b200 import _C
+    from .hostsim import harness
+    old = _C._lib
+    _C._lib = harness.get()
+    yield _C._lib
+    _C._lib = old
+
+
+def test_hash_indices_bit_exact(hostsim_lib):
+    from levels2fm_b200 import ops
+    from oracle import hashgrid
+    cfg = port.SceneCfg()
+    meta = cfg.grid()
+    grid = ops.GridSpec(16, 2, 19, 16, cfg.per_level_scale).resolve(hostsim_lib)
+    g = torch.Generator().manual_seed(0)
+    u = torch.rand(3000, 3, generator=g)
+    u[:300] = u[:300] * 3 - 1
+    u[300:600] = torch.round(u[300:600] * 64) / 64
+    table = torch.randn(meta.n_params, generator=g)
+    enc, idx = ops.grid_encode_raw(hostsim_lib, grid, table, u, want_idx=True)
+    for l, lv in enumerate(meta.levels):
+        ref_idx, _ = hashgrid.corner_indices(u, lv)
+        assert torch.equal(idx[:, l, :].to(torch.int64) & 0xFFFFFFFF, ref_idx + lv.offset)
+    ref = hashgrid.encode(u, table, meta)
+    assert (enc - ref).abs().max() <= 1e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("dataset,n_levels,layers,n_samples,n_rays,dual", [
+    ("DTU", 4, (None, 64, 16), 16, 9, False),
+    ("ETH3D", 16, (None, 64, 64, 64, 16), 24, 5, False),
+    ("bmvs", 16, (None, 64, 16), 12, 4, True),
+    ("DTU", 16, (None, 64, 64, 16), 33, 3, False),
+])
+def test_render_forward_backward_matches_oracle(dataset, n_levels, layers, n_samples, n_rays, dual):
+    opt = common.make_opt(dataset, "cpu", n_levels, layers, n_samples, dual)
+    outs, grads = common.render_parity_case(opt, n_levels, 2, n_rays)
+    for k, (a, b) in outs.items():
+        assert common.rel_err(a, b) < 1e-4, k
+    for k, (a, b) in grads.items():
+        assert common.cosine(a, b) > 1 - 1e-6, k
+        assert common.rel_err(a, b) < 2e-3, (k, common.rel_err(a, b))
+
+
+def test_golden_c1_through_kernels():
+    gold = gc.load("c1_render.npz")
+    out, grads, loss = gc.run_c1_product(gold, "cpu")
+    gc.check_c1(out, grads, loss, gold)
+
+
+def test_golden_sphere_tracing_through_kernels():
+    gold = gc.load("st_dtu.npz")
+    gc.check_st(*gc.run_st_product(gold, "cpu"), gold)
+
+
+def test_ragged_and_tiny_inputs():
+    """n not a multiple of the 8-sample warp tile / 64-sample CTA step; a single point; zero points."""
+    opt = common.make_opt("DTU", "cpu", 4, (None, 64, 16), 16)
+    cfg = common.cfg_of(opt, 4)
+    sdf_sd, _ = port.random_state(cfg, seed=2, table_std=0.2)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    g = torch.Generator().manual_seed(0)
+    for n in (1, 7, 65, 130):
+        x = torch.rand(n, 3, generator=g) * 1.6 - 0.8
+        s, f = sdf.infer_sdf(x, mode="ret_all")
+        rs, rf = port.infer_sdf(x, sdf_sd, cfg, "ret_all")
+        assert common.rel_err(s, rs) < 1e-5 and common.rel_err(f, rf) < 1e-5
+        n_ours = sdf.gradient(x.clone())
+        n_ref = port.sdf_gradient(x.clone(), sdf_sd, cfg)
+        assert common.rel_err(n_ours, n_ref.detach()) < 1e-5
+    assert sdf.infer_sdf(torch.zeros(0, 3)).shape == (0, 1)
+    assert sdf.infer_sdf(torch.zeros(2, 5, 3)).shape == (2, 5, 1)
