@@ -78,12 +78,14 @@ typedef struct {
     const float* ray;     /* device [n_rays,3]  un-normalised direction (ray mode) */
     const float* t;       /* device [n_rays,n_per_ray] depths; x = center + ray*t (mul then add, as torch) */
     const int32_t* ray_index; /* device [n_rays] nullable: compacted list of ray ids to process (ray mode) */
-    const int32_t* n_active;  /* device scalar nullable: number of valid entries in ray_index */
+    const int32_t* n_active;  /* device scalar nullable: number of rays to process (entries of ray_index), read on the device */
     int64_t n;            /* explicit mode: number of points; ray mode: n_rays * n_per_ray */
     int32_t n_rays;
     int32_t n_per_ray;
     int32_t t_stride;     /* row stride of t (>= n_per_ray) */
     int32_t t_offset;     /* first column of t to use */
+    int32_t out_stride;   /* ray mode, 0 = dense: per-sample outputs of sample j of ray r go to index r*out_stride + out_offset + j */
+    int32_t out_offset;
 } ls2fm_points_t;
 
 /* The radiance decoder (models/base.py:221-261).  The reference applies NO hidden
@@ -174,6 +176,26 @@ int ls2fm_composite_backward(const float* ray, const float* t, const float* sdf,
 int ls2fm_sample_uniform(const float* center, const float* ray, int32_t n_rays, int32_t n_samples,
                          const float bound_min[3], const float bound_max[3],
                          float* t, float* hits_t, void* stream);
+
+/* Error-bounded (VolSDF) sampler, models/Renderer.py:186-328 with the SURVEY 8(a) a5 fixes.
+ * The caller provides the device workspace (ls2fm_sampler_workspace_bytes).  Outputs: t [R, N+Nf] sorted,
+ * beta_plus [R] (network beta for converged rays), iters [R] (round of convergence, -1 = gave up); the last two
+ * nullable.  No host synchronisation: active rays are compacted on the device between rounds and the SDF of the
+ * newly drawn samples is evaluated by the fused field kernel on the compacted list only. */
+typedef struct {
+    int32_t n_samples;        /* sample_intvs N */
+    int32_t n_final;          /* final_sample_intvs Nf */
+    int32_t max_upsample_iter;
+    int32_t max_bisection_itr;
+    float eps;
+    float beta_speed;
+} ls2fm_sampler_cfg_t;
+int64_t ls2fm_sampler_workspace_bytes(const ls2fm_sampler_cfg_t* cfg, int32_t n_rays);
+int ls2fm_sample_error_bounded(const ls2fm_field_t* sdf_field, const float* beta_param,
+                               const ls2fm_sampler_cfg_t* cfg,
+                               const float* center, const float* ray, int32_t n_rays,
+                               void* workspace, float* t_out, float* beta_plus, float* iters,
+                               void* stream);
 
 #ifdef __cplusplus
 }

@@ -45,7 +45,13 @@ class Field(C.Structure):
 class Points(C.Structure):
     _fields_ = [("xyz", C.c_void_p), ("center", C.c_void_p), ("ray", C.c_void_p), ("t", C.c_void_p),
                 ("ray_index", C.c_void_p), ("n_active", C.c_void_p), ("n", C.c_int64),
-                ("n_rays", C.c_int32), ("n_per_ray", C.c_int32), ("t_stride", C.c_int32), ("t_offset", C.c_int32)]
+                ("n_rays", C.c_int32), ("n_per_ray", C.c_int32), ("t_stride", C.c_int32), ("t_offset", C.c_int32),
+                ("out_stride", C.c_int32), ("out_offset", C.c_int32)]
+
+
+class SamplerCfg(C.Structure):
+    _fields_ = [("n_samples", C.c_int32), ("n_final", C.c_int32), ("max_upsample_iter", C.c_int32),
+                ("max_bisection_itr", C.c_int32), ("eps", C.c_float), ("beta_speed", C.c_float)]
 
 
 class Radiance(C.Structure):
@@ -57,6 +63,7 @@ _F3 = C.c_float * 3
 _VP = C.c_void_p
 
 # name -> (restype, argtypes); every symbol include/ls2fm.h declares
+# (SamplerCfg is defined above Radiance)
 SIGNATURES = {
     "ls2fm_abi_version": (C.c_int, []),
     "ls2fm_last_error": (C.c_char_p, []),
@@ -70,6 +77,8 @@ SIGNATURES = {
     "ls2fm_composite_forward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 5),
     "ls2fm_composite_backward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 9),
     "ls2fm_sample_uniform": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _F3, _F3, _VP, _VP, _VP]),
+    "ls2fm_sampler_workspace_bytes": (C.c_int64, [C.POINTER(SamplerCfg), C.c_int32]),
+    "ls2fm_sample_error_bounded": (C.c_int, [C.POINTER(Field), _VP, C.POINTER(SamplerCfg), _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP]),
 }
 
 

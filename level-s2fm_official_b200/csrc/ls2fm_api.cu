@@ -7,6 +7,7 @@
 
 #include "ls2fm_field.cuh"
 #include "ls2fm_render.cuh"
+#include "ls2fm_sampler.cuh"
 
 static thread_local std::string g_err;
 
@@ -218,6 +219,7 @@ int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, 
     if (ls_check_field(field) || ls_check_points(pts)) return 1;
     if (pts->n == 0) return 0;
     if (rad && ls_check_rad(rad, field, pts)) return 1;
+    if (pts->ray_index || pts->n_active || pts->out_stride) return ls_fail("field_backward: compacted ray lists are forward-only");
     if (rad && g_rgb && (!saved_nrm || !saved_rgb)) return ls_fail("field_backward: saved_nrm / saved_rgb required with radiance");
     if (!rad && (g_rgb || d_w_eff || d_b_eff || d_geo2)) return ls_fail("field_backward: radiance gradients need the radiance block");
     if (pts->n == 0) return 0;
@@ -268,6 +270,76 @@ int ls2fm_composite_backward(const float* ray, const float* t, const float* sdf,
               beta_param, beta_speed, bgcolor[0], bgcolor[1], bgcolor[2], n_rays, n_samples, g_rgb, g_depth, g_normal, d_sdf,
               d_rgbs, d_nrm, d_beta_param, d_ray);
     return ls_check_launch("composite_backward");
+}
+
+// workspace carving for the error-bounded sampler (all 16-byte aligned)
+struct LsSamplerWs { size_t D, S, beta_plus, fine, iters, state, cnt, ray_index, hits, total; };
+static LsSamplerWs ls_sampler_ws(const ls2fm_sampler_cfg_t* c, int32_t R) {
+    LsSamplerWs w;
+    const size_t Mmax = (size_t)c->n_samples * (c->max_upsample_iter + 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+    w.D = take((size_t)R * Mmax * 4); w.S = take((size_t)R * Mmax * 4);
+    w.beta_plus = take((size_t)R * 4); w.fine = take((size_t)R * c->n_final * 4); w.iters = take((size_t)R * 4);
+    w.state = take((size_t)R * 4); w.cnt = take((size_t)(c->max_upsample_iter + 2) * 4);
+    w.ray_index = take((size_t)(c->max_upsample_iter + 2) * R * 4); w.hits = take((size_t)R * 8);
+    w.total = off;
+    return w;
+}
+
+int64_t ls2fm_sampler_workspace_bytes(const ls2fm_sampler_cfg_t* cfg, int32_t n_rays) {
+    if (!cfg || n_rays < 0 || cfg->n_samples < 2 || cfg->max_upsample_iter < 0) return -1;
+    return (int64_t)ls_sampler_ws(cfg, n_rays).total;
+}
+
+int ls2fm_sample_error_bounded(const ls2fm_field_t* sdf_field, const float* beta_param, const ls2fm_sampler_cfg_t* cfg,
+                               const float* center, const float* ray, int32_t n_rays, void* workspace, float* t_out,
+                               float* beta_plus, float* iters, void* stream) {
+    if (ls_check_field(sdf_field)) return 1;
+    if (!cfg || cfg->n_samples < 2 || cfg->n_final < 1 || cfg->max_upsample_iter < 0 || cfg->max_bisection_itr < 0)
+        return ls_fail("sample_error_bounded: bad sampler config");
+    if (n_rays < 0 || (n_rays > 0 && (!center || !ray || !beta_param || !workspace || !t_out)))
+        return ls_fail("sample_error_bounded: NULL argument");
+    if (n_rays == 0) return 0;
+    const LsSamplerWs w = ls_sampler_ws(cfg, n_rays);
+    char* base = (char*)workspace;
+    LsSamplerArgs a;
+    memset(&a, 0, sizeof(a));
+    a.center = center; a.ray = ray; a.beta_param = beta_param;
+    a.n_rays = n_rays; a.N = cfg->n_samples; a.Nf = cfg->n_final; a.max_iter = cfg->max_upsample_iter;
+    a.max_bisect = cfg->max_bisection_itr; a.Mmax = cfg->n_samples * (cfg->max_upsample_iter + 1);
+    a.eps = cfg->eps; a.beta_speed = cfg->beta_speed;
+    a.cx = (sdf_field->bound_max[0] + sdf_field->bound_min[0]) / 2.f; a.hx = (sdf_field->bound_max[0] - sdf_field->bound_min[0]) / 2.f;
+    a.cy = (sdf_field->bound_max[1] + sdf_field->bound_min[1]) / 2.f; a.hy = (sdf_field->bound_max[1] - sdf_field->bound_min[1]) / 2.f;
+    a.cz = (sdf_field->bound_max[2] + sdf_field->bound_min[2]) / 2.f; a.hz = (sdf_field->bound_max[2] - sdf_field->bound_min[2]) / 2.f;
+    a.D = (float*)(base + w.D); a.S = (float*)(base + w.S); a.beta_plus = (float*)(base + w.beta_plus);
+    a.fine = (float*)(base + w.fine); a.iters = (float*)(base + w.iters); a.state = (int*)(base + w.state);
+    a.cnt = (int*)(base + w.cnt); a.ray_index = (int*)(base + w.ray_index); a.hits = (float*)(base + w.hits);
+
+    const int wpb = 4;
+    const unsigned grid = (unsigned)((n_rays + wpb - 1) / wpb);
+    const int smem_round = wpb * 5 * a.Mmax * (int)sizeof(float);
+    const int smem_final = wpb * (a.N + a.Nf) * (int)sizeof(float);
+    if (smem_round > ls_max_smem()) return ls_fail("sample_error_bounded: too many samples per ray for shared memory");
+    if (ls_opt_in_smem(ls_sampler_round_kernel, smem_round)) return 1;
+    LS_LAUNCH(ls_sampler_init_kernel, grid, wpb * 32, 0, stream, a);
+    if (ls_check_launch("sampler_init")) return 1;
+    ls2fm_points_t p;
+    memset(&p, 0, sizeof(p));
+    p.center = center; p.ray = ray; p.t = a.D;
+    p.n_rays = n_rays; p.n_per_ray = a.N; p.n = (int64_t)n_rays * a.N;
+    p.t_stride = a.Mmax; p.out_stride = a.Mmax;
+    for (int it = 0; it <= a.max_iter; ++it) {
+        // SDF of the samples drawn for this round, on the compacted list of rays that asked for them
+        p.t_offset = a.N * it; p.out_offset = a.N * it;
+        p.ray_index = a.ray_index + (size_t)it * n_rays;
+        p.n_active = a.cnt + it;
+        if (ls2fm_field_forward(sdf_field, &p, nullptr, nullptr, a.S, nullptr, nullptr, stream)) return 1;
+        LS_LAUNCH(ls_sampler_round_kernel, grid, wpb * 32, smem_round, stream, a, it);
+        if (ls_check_launch("sampler_round")) return 1;
+    }
+    LS_LAUNCH(ls_sampler_finalize_kernel, grid, wpb * 32, smem_final, stream, a, t_out, beta_plus, iters);
+    return ls_check_launch("sampler_finalize");
 }
 
 }  // extern "C"

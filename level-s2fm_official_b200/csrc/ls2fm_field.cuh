@@ -187,8 +187,10 @@ LS_DEV void ls_stage_weights(const LsFieldArgs& a, float* smem) {
     }
 }
 
-// sample position: explicit xyz or center + ray * t (mul, then add: models/camera.py:262-266 / torch eager)
-LS_DEV void ls_sample_point(const ls2fm_points_t& p, int64_t i, float x[3], int* ray_id) {
+// sample position: explicit xyz or center + ray * t (mul, then add: utils/camera.py:262-266 / torch eager).
+// *out_i: where the per-sample outputs of sample i go (dense, or r * out_stride + out_offset + j for compacted rays)
+LS_DEV void ls_sample_point(const ls2fm_points_t& p, int64_t i, float x[3], int* ray_id, int64_t* out_i) {
+    *out_i = i;
     if (p.xyz) {
         x[0] = __ldg(p.xyz + 3 * i); x[1] = __ldg(p.xyz + 3 * i + 1); x[2] = __ldg(p.xyz + 3 * i + 2);
         *ray_id = p.n_per_ray > 0 ? (int)(i / p.n_per_ray) : 0;
@@ -200,7 +202,16 @@ LS_DEV void ls_sample_point(const ls2fm_points_t& p, int64_t i, float x[3], int*
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[d] = ls_fadd(__ldg(p.center + 3 * r + d), ls_fmul(__ldg(p.ray + 3 * r + d), t));
         *ray_id = r;
+        if (p.out_stride > 0) *out_i = (int64_t)r * p.out_stride + p.out_offset + j;
     }
+}
+// number of samples to process: all, or (device-side count of compacted rays) * n_per_ray
+LS_DEV int64_t ls_n_samples(const ls2fm_points_t& p) {
+    if (p.n_active) {
+        const int64_t m = (int64_t)__ldg(p.n_active) * p.n_per_ray;
+        return m < p.n ? m : p.n;
+    }
+    return p.n;
 }
 
 // one level of the hash grid at u: features h[2] and dh/du [2][3]
@@ -249,14 +260,16 @@ __global__ void __launch_bounds__(512, 1) ls_field_forward_kernel(const LsFieldA
     const int og = lane & 15, sg = lane >> 4;         // matrix mapping
     const bool need_nrm = a.out_nrm != nullptr || a.r.w_eff != nullptr;
 
-    const int64_t n_tiles = (a.p.n + LS_WS - 1) / LS_WS;
+    const int64_t n_pts = ls_n_samples(a.p);
+    const int64_t n_tiles = (n_pts + LS_WS - 1) / LS_WS;
     for (int64_t tile = (int64_t)blockIdx.x * nw + warp; tile < n_tiles; tile += (int64_t)gridDim.x * nw) {
         // ------------------------------------------------ phase 1: points + hash-grid gather
-        const int64_t i = tile * LS_WS + s8;
-        const bool valid = i < a.p.n;
+        const int64_t i_in = tile * LS_WS + s8;
+        const bool valid = i_in < n_pts;
         float x[3] = {0.f, 0.f, 0.f}, u[3];
         int ray_id = 0;
-        if (valid) ls_sample_point(a.p, i, x, &ray_id);
+        int64_t i = i_in;
+        if (valid) ls_sample_point(a.p, i_in, x, &ray_id, &i);
         ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
         float J[4][2][3];
 #pragma unroll
@@ -504,11 +517,12 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
     const int64_t n_ctiles = (a.p.n + LS_WS * LS_BW_WARPS - 1) / (LS_WS * LS_BW_WARPS);
     for (int64_t ct = blockIdx.x; ct < n_ctiles; ct += gridDim.x) {
         // ------------------------------------------------ B1: upstream gradients of this sample
-        const int64_t i = (ct * LS_BW_WARPS + warp) * LS_WS + s8;
-        const bool valid = i < a.p.n;
+        const int64_t i_in = (ct * LS_BW_WARPS + warp) * LS_WS + s8;
+        const bool valid = i_in < a.p.n;
         float x[3] = {0.f, 0.f, 0.f}, u[3];
         int ray_id = 0;
-        if (valid) ls_sample_point(a.p, i, x, &ray_id);
+        int64_t i = i_in;
+        if (valid) ls_sample_point(a.p, i_in, x, &ray_id, &i);
         ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
         float pbar[3] = {0.f, 0.f, 0.f};
         float nbar[3] = {0.f, 0.f, 0.f};

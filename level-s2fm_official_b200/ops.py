@@ -391,3 +391,22 @@ class GridEncode(torch.autograd.Function):
         d_u = torch.zeros_like(u) if ctx.needs_input_grad[2] else None
         grid_encode_backward_raw(lib, ctx.grid, table, u, g_enc.contiguous(), d_table, d_u)
         return None, d_table, d_u
+
+
+def sample_error_bounded_raw(lib, spec: FieldSpec, table, theta, beta_param, center, ray, n_samples, n_final,
+                             max_upsample_iter, max_bisection_itr, eps, beta_speed):
+    """Renderer.volsdf_sampling's error-bounded branch -> (t [R, N+Nf], beta_plus [R], iters [R])."""
+    r = center.numel() // 3
+    dev = center.device
+    cfg = _C.SamplerCfg(int(n_samples), int(n_final), int(max_upsample_iter), int(max_bisection_itr), float(eps), float(beta_speed))
+    nbytes = int(lib.dll.ls2fm_sampler_workspace_bytes(cfg, r))
+    if nbytes < 0:
+        raise RuntimeError("bad sampler configuration")
+    ws = torch.empty(max(nbytes, 16) // 4 + 4, dtype=torch.float32, device=dev)
+    t = torch.empty(r, n_samples + n_final, device=dev)
+    beta_plus = torch.empty(r, device=dev)
+    iters = torch.empty(r, device=dev)
+    f = spec.c_field(lib, table, theta)
+    _call(lib, "sample_error_bounded", lib.dll.ls2fm_sample_error_bounded, f, lib.ptr(beta_param), cfg, lib.ptr(center), lib.ptr(ray),
+          r, lib.ptr(ws), lib.ptr(t), lib.ptr(beta_plus), lib.ptr(iters), lib.stream())
+    return t, beta_plus, iters

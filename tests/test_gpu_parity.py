@@ -85,6 +85,16 @@ def test_golden_sphere_tracing_and_surface_points():
     gc.check_st(*gc.run_st_product(gold, DEV), gold)
 
 
+def test_golden_error_bounded_sampler():
+    gold = gc.load("c2_sampler.npz")
+    gc.check_c2(*gc.run_c2_product(gold, DEV), gold)
+
+
+@pytest.mark.parametrize("eps,N,std", [(0.002, 16, 0.05), (0.02, 32, 0.1)])
+def test_error_bounded_sampler_hard_cases(eps, N, std):
+    gc.sampler_hard_case(DEV, eps, N, std)
+
+
 def test_ragged_tiny_and_empty_inputs():
     opt = common.make_opt("DTU", DEV, 4, (None, 64, 16), 16)
     cfg = common.cfg_of(opt, 4)

@@ -84,3 +84,13 @@ def test_ragged_and_tiny_inputs():
         assert common.rel_err(n_ours, n_ref.detach()) < 1e-5
     assert sdf.infer_sdf(torch.zeros(0, 3)).shape == (0, 1)
     assert sdf.infer_sdf(torch.zeros(2, 5, 3)).shape == (2, 5, 1)
+
+
+def test_golden_error_bounded_sampler_through_kernels():
+    gold = gc.load("c2_sampler.npz")
+    gc.check_c2(*gc.run_c2_product(gold, "cpu"), gold)
+
+
+@pytest.mark.parametrize("eps,N,std", [(0.002, 16, 0.05), (0.02, 32, 0.1)])
+def test_error_bounded_sampler_hard_cases(eps, N, std):
+    gc.sampler_hard_case("cpu", eps, N, std)
