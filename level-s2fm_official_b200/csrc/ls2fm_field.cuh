@@ -124,12 +124,12 @@ LS_DEV void ls_prod_fwd(const float* Wt, int pitch, int n_in, const float* in0, 
 
 // acc[q][s] = sum_j Wt[og + 16 q][j] * z[j][s]      (interleaved ownership: inputs og, og+16, og+32, og+48)
 // n_j: number of valid j (multiple of 4); rows >= n_rows are clamped (their results are discarded).
-template <int NCH>
+template <int NCH, int NQ>
 LS_DEV void ls_prod_rev(const float* Wt, int pitch, int n_rows, int n_j, const float* z0, const float* z1, int R,
                         int sg, int og, float (&acc0)[4][4], float (&acc1)[4][4]) {
-    const float* wr[4];
+    const float* wr[NQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
         int row = og + 16 * q;
         row = row < n_rows ? row : n_rows - 1;
         wr[q] = Wt + row * pitch;
@@ -138,16 +138,16 @@ LS_DEV void ls_prod_rev(const float* Wt, int pitch, int n_rows, int n_j, const f
     const float* p1 = z1 + sg * R * 4;
 #pragma unroll 2
     for (int j = 0; j < n_j; j += 4) {
-        float4 w[4];
+        float4 w[NQ];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w[q] = ls_ld4(wr[q] + j);
+        for (int q = 0; q < NQ; ++q) w[q] = ls_ld4(wr[q] + j);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const float4 a = ls_ld4(p0 + 4 * (j + jj));
             float4 b = a;
             if (NCH == 2) b = ls_ld4(p1 + 4 * (j + jj));
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < NQ; ++q) {
                 const float wv = jj == 0 ? w[q].x : jj == 1 ? w[q].y : jj == 2 ? w[q].z : w[q].w;
                 acc0[q][0] = fmaf(wv, a.x, acc0[q][0]); acc0[q][1] = fmaf(wv, a.y, acc0[q][1]);
                 acc0[q][2] = fmaf(wv, a.z, acc0[q][2]); acc0[q][3] = fmaf(wv, a.w, acc0[q][3]);
@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(512, 1) ls_field_forward_kernel(const LsFieldA
                     for (int s = 0; s < 4; ++s) acc[q][s] = 0.f;
                 const float* Z = A + l * LS_WS * LS_H;         // w_{l+1}
                 const int n_rows = a.f.dims[l];
-                ls_prod_rev<1>(smem + a.net.sw_off[l], a.net.pitch[l], n_rows, LS_H, Z, Z, LS_H, sg, og, acc, dummy);
+                if (l > 0) ls_prod_rev<1, 4>(smem + a.net.sw_off[l], a.net.pitch[l], n_rows, LS_H, Z, Z, LS_H, sg, og, acc, dummy);
+                else ls_prod_rev<1, 3>(smem + a.net.sw_off[l], a.net.pitch[l], n_rows, LS_H, Z, Z, LS_H, sg, og, acc, dummy);   // 35 rows < 48
                 if (l > 0) {
                     float* AL = A + (l - 1) * LS_WS * LS_H;
 #pragma unroll
@@ -738,7 +739,7 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                         for (int p = 0; p < 4; ++p)
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                wacc[l][p][q] += iv[p].x * zv[q].x + iv[p].y * zv[q].y + iv[p].z * zv[q].z + iv[p].w * zv[q].w;
+                                wacc[l][p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wacc[l][p][q]))));
                         if (TAN) {
 #pragma unroll
                             for (int p = 0; p < 4; ++p) iv[p] = ls_ld4(ls_row(base + o_ind, R_in, h2, rin[p]));
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                             for (int p = 0; p < 4; ++p)
 #pragma unroll
                                 for (int q = 0; q < 4; ++q)
-                                    wacc[l][p][q] += iv[p].x * zv[q].x + iv[p].y * zv[q].y + iv[p].z * zv[q].z + iv[p].w * zv[q].w;
+                                    wacc[l][p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wacc[l][p][q]))));
                         }
                         const float4 bz = ls_ld4(ls_row(base + o_z, LS_H, h2, brow));
                         bsum += bz.x + bz.y + bz.z + bz.w;
@@ -762,8 +763,10 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int s = 0; s < 4; ++s) { acc[q][s] = 0.f; accd[q][s] = 0.f; }
-            ls_prod_rev<TAN ? 2 : 1>(smem + a.net.sw_off[l], a.net.pitch[l], n_in, last ? LS_OROWS : LS_H,
-                                     my + o_z, my + o_zd, LS_H, sg, og, acc, accd);
+            if (l > 0) ls_prod_rev<TAN ? 2 : 1, 4>(smem + a.net.sw_off[l], a.net.pitch[l], n_in, last ? LS_OROWS : LS_H,
+                                                   my + o_z, my + o_zd, LS_H, sg, og, acc, accd);
+            else ls_prod_rev<TAN ? 2 : 1, 3>(smem + a.net.sw_off[l], a.net.pitch[l], n_in, last ? LS_OROWS : LS_H,
+                                             my + o_z, my + o_zd, LS_H, sg, og, acc, accd);
             __syncthreads();     // everybody is done reading the activations of layer l
             // ---- (c) through the activation (in place) or out to the encoding adjoints
             if (l > 0) {
@@ -779,8 +782,8 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                     const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
-                        const float qv = expf(-sp_beta * aa[s]);          // 1 - phi'
-                        const float d1 = ls_softplus_d1_from_a(aa[s], sp_beta);
+                        const float qv = LS_FAST_EXP(-sp_beta * aa[s]);   // 1 - phi'
+                        const float d1 = 1.f - qv;
                         zb[s] = d1 * acc[q][s];
                         if (TAN) { zb[s] += sp_beta * qv * dd[s] * accd[q][s]; zd[s] = d1 * accd[q][s]; }
                     }

