@@ -197,6 +197,17 @@ int ls2fm_sample_error_bounded(const ls2fm_field_t* sdf_field, const float* beta
                                void* workspace, float* t_out, float* beta_plus, float* iters,
                                void* stream);
 
+/* ------------------------------------------------------------------ sphere tracing
+ * The no-grad march of SDF.sphere_tracing (models/SDF.py:116-200) as one kernel: both fronts, thresholding, clamping to
+ * t_far, crossing test; every ray marches independently with the fused field evaluation inside the loop.
+ *   track        [m, iters_max, 3]  start-front point before step k
+ *   n_unfinished [iters_max + 1]    unfinished start fronts at the top of iteration k (zeroed by the call);
+ *                                   K = first k with n_unfinished[k] == 0 (else iters_max) is the reference's iteration count
+ *   t_near, t_far [m];  acc_end [iters_max + 1, m]  end-front depth at the top of iteration k (use row K). */
+int ls2fm_sphere_trace(const ls2fm_field_t* sdf_field, const float* ray0, const float* ray_dir, int64_t m,
+                       float sdf_threshold, int32_t iters_max, float* track, int32_t* n_unfinished,
+                       float* t_near, float* t_far, float* acc_end, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

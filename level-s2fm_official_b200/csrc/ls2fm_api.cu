@@ -8,6 +8,7 @@
 #include "ls2fm_field.cuh"
 #include "ls2fm_render.cuh"
 #include "ls2fm_sampler.cuh"
+#include "ls2fm_trace.cuh"
 
 static thread_local std::string g_err;
 
@@ -21,7 +22,9 @@ static int ls_sm_count() { return 2; }
 static int ls_max_smem() { return 227 * 1024; }
 template <class K> static int ls_opt_in_smem(K, int) { return 0; }
 static int ls_check_launch(const char*) { return 0; }
+static void ls_memset_async(void* p, int v, size_t n, void*) { memset(p, v, n); }
 #else
+static void ls_memset_async(void* p, int v, size_t n, void* stream) { cudaMemsetAsync(p, v, n, (cudaStream_t)stream); }
 static int ls_sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -340,6 +343,43 @@ int ls2fm_sample_error_bounded(const ls2fm_field_t* sdf_field, const float* beta
     }
     LS_LAUNCH(ls_sampler_finalize_kernel, grid, wpb * 32, smem_final, stream, a, t_out, beta_plus, iters);
     return ls_check_launch("sampler_finalize");
+}
+
+int ls2fm_sphere_trace(const ls2fm_field_t* sdf_field, const float* ray0, const float* ray_dir, int64_t m, float sdf_threshold,
+                       int32_t iters_max, float* track, int32_t* n_unfinished, float* t_near, float* t_far, float* acc_end,
+                       void* stream) {
+    if (ls_check_field(sdf_field)) return 1;
+    if (m < 0 || iters_max < 1 || iters_max > 1024) return ls_fail("sphere_trace: bad m / iters_max");
+    if (m > 0 && (!ray0 || !ray_dir || !track || !n_unfinished || !t_near || !t_far || !acc_end))
+        return ls_fail("sphere_trace: NULL argument");
+    ls_memset_async(n_unfinished, 0, sizeof(int32_t) * (size_t)(iters_max + 1), stream);
+    if (m == 0) return 0;
+    LsTraceArgs t;
+    memset(&t, 0, sizeof(t));
+    ls2fm_points_t pts;
+    memset(&pts, 0, sizeof(pts));
+    ls_fill_args(t.fa, sdf_field, &pts, nullptr);
+    t.ray0 = ray0; t.dir = ray_dir; t.m = m;
+    t.cx = (sdf_field->bound_max[0] + sdf_field->bound_min[0]) / 2.f; t.hx = (sdf_field->bound_max[0] - sdf_field->bound_min[0]) / 2.f;
+    t.cy = (sdf_field->bound_max[1] + sdf_field->bound_min[1]) / 2.f; t.hy = (sdf_field->bound_max[1] - sdf_field->bound_min[1]) / 2.f;
+    t.cz = (sdf_field->bound_max[2] + sdf_field->bound_min[2]) / 2.f; t.hz = (sdf_field->bound_max[2] - sdf_field->bound_min[2]) / 2.f;
+    t.thr = sdf_threshold; t.iters_max = iters_max;
+    t.track = track; t.cnt = n_unfinished; t.t_near = t_near; t.t_far = t_far; t.acc_e_hist = acc_end;
+    const int64_t n_tiles = (m + 3) / 4;
+    // few rays: spread the tiles over the SMs (one warp tile = 4 rays), at most 16 warps per CTA
+    int nw = 16;
+    while (nw > 1 && (n_tiles + nw - 1) / nw < ls_sm_count()) nw >>= 1;
+    for (;; nw >>= 1) {
+        t.fa.net = ls_plan_net(*sdf_field, 0, nw, false);
+        if (t.fa.net.total * (int)sizeof(float) <= ls_max_smem()) break;
+        if (nw <= 1) return ls_fail("sphere_trace: network does not fit in shared memory");
+    }
+    const int smem = t.fa.net.total * (int)sizeof(float);
+    if (ls_opt_in_smem(ls_sphere_trace_kernel, smem)) return 1;
+    int64_t grid = (n_tiles + nw - 1) / nw;
+    if (grid > ls_sm_count()) grid = ls_sm_count();
+    LS_LAUNCH(ls_sphere_trace_kernel, (unsigned)grid, nw * 32, smem, stream, t);
+    return ls_check_launch("sphere_trace");
 }
 
 }  // extern "C"

@@ -242,6 +242,63 @@ LS_DEV void ls_level_eval(const ls2fm_field_t& f, int l, const float u[3], float
     }
 }
 
+// MLP forward of one warp tile: E (encoding rows) -> A_k = softplus(z_k) (k = 1..K-1, kept for the reverse sweep) -> Y
+LS_DEV void ls_mlp_forward(const LsFieldArgs& a, const float* smem, const float* E, float* A, float* Y, int og, int sg) {
+    const int K = a.f.n_layers;
+    const float sp_beta = a.f.softplus_beta, sp_thr = a.f.softplus_threshold;
+    const float* in = E;
+    int R = LS_EROWS, n_in = a.f.dims[0];
+    for (int l = 0; l < K - 1; ++l) {
+        float acc[4][4], dummy[4][4];
+        const float4 b = ls_ld4(smem + a.net.sb_off[l] + 4 * og);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { acc[0][s] = b.x; acc[1][s] = b.y; acc[2][s] = b.z; acc[3][s] = b.w; }
+        ls_prod_fwd<1>(smem + a.net.sw_off[l], a.net.pitch[l], n_in, in, in, R, sg, og, acc, dummy);
+        float* out = A + l * LS_WS * LS_H;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 o;
+            o.x = ls_softplus(acc[q][0], sp_beta, sp_thr); o.y = ls_softplus(acc[q][1], sp_beta, sp_thr);
+            o.z = ls_softplus(acc[q][2], sp_beta, sp_thr); o.w = ls_softplus(acc[q][3], sp_beta, sp_thr);
+            ls_st4(ls_row(out, LS_H, sg, 4 * og + q), o);
+        }
+        __syncwarp();
+        in = out; R = LS_H; n_in = LS_H;
+    }
+    if (og < LS_OROWS / 4) {
+        float acc[4][4], dummy[4][4];
+        const float4 b = ls_ld4(smem + a.net.sb_off[K - 1] + 4 * og);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { acc[0][s] = b.x; acc[1][s] = b.y; acc[2][s] = b.z; acc[3][s] = b.w; }
+        ls_prod_fwd<1>(smem + a.net.sw_off[K - 1], a.net.pitch[K - 1], n_in, in, in, R, sg, og, acc, dummy);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            ls_st4(ls_row(Y, LS_OROWS, sg, 4 * og + q), make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]));
+    }
+    __syncwarp();
+}
+
+// hash-grid features of x into the encoding rows of a warp tile (no Jacobian): lane = (sample s8, level group g)
+LS_DEV void ls_encode_tile(const LsFieldArgs& a, float* E, const float x[3], int s8, int g) {
+    float u[3];
+    ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int l = g + 4 * r;
+        if (l < a.f.n_levels) {
+            float h[2], dh[2][3];
+            ls_level_eval(a.f, l, u, h, dh);
+            ls_el(E, LS_EROWS, 3 + 2 * l, s8) = h[0];
+            ls_el(E, LS_EROWS, 3 + 2 * l + 1, s8) = h[1];
+        }
+    }
+    if (g == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ls_el(E, LS_EROWS, d, s8) = ls_fdiv(x[d], a.f.rescale);
+    }
+    __syncwarp();
+}
+
 // ================================================================ forward kernel
 // grid: persistent, blockDim = 32 * n_warps; every warp walks tiles independently.
 __global__ void __launch_bounds__(512, 1) ls_field_forward_kernel(const LsFieldArgs a) {
@@ -298,38 +355,7 @@ __global__ void __launch_bounds__(512, 1) ls_field_forward_kernel(const LsFieldA
         __syncwarp();
 
         // ------------------------------------------------ phase 2: MLP forward
-        {
-            const float* in = E;
-            int R = LS_EROWS, n_in = din0;
-            for (int l = 0; l < K - 1; ++l) {
-                float acc[4][4], dummy[4][4];
-                const float4 b = ls_ld4(smem + a.net.sb_off[l] + 4 * og);
-#pragma unroll
-                for (int s = 0; s < 4; ++s) { acc[0][s] = b.x; acc[1][s] = b.y; acc[2][s] = b.z; acc[3][s] = b.w; }
-                ls_prod_fwd<1>(smem + a.net.sw_off[l], a.net.pitch[l], n_in, in, in, R, sg, og, acc, dummy);
-                float* out = A + l * LS_WS * LS_H;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 o;
-                    o.x = ls_softplus(acc[q][0], sp_beta, sp_thr); o.y = ls_softplus(acc[q][1], sp_beta, sp_thr);
-                    o.z = ls_softplus(acc[q][2], sp_beta, sp_thr); o.w = ls_softplus(acc[q][3], sp_beta, sp_thr);
-                    ls_st4(ls_row(out, LS_H, sg, 4 * og + q), o);
-                }
-                __syncwarp();
-                in = out; R = LS_H; n_in = LS_H;
-            }
-            if (og < LS_OROWS / 4) {
-                float acc[4][4], dummy[4][4];
-                const float4 b = ls_ld4(smem + a.net.sb_off[K - 1] + 4 * og);
-#pragma unroll
-                for (int s = 0; s < 4; ++s) { acc[0][s] = b.x; acc[1][s] = b.y; acc[2][s] = b.z; acc[3][s] = b.w; }
-                ls_prod_fwd<1>(smem + a.net.sw_off[K - 1], a.net.pitch[K - 1], n_in, in, in, R, sg, og, acc, dummy);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    ls_st4(ls_row(Y, LS_OROWS, sg, 4 * og + q), make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]));
-            }
-            __syncwarp();
-        }
+        ls_mlp_forward(a, smem, E, A, Y, og, sg);
 
         // ------------------------------------------------ phase 3: reverse sweep for d(sdf)/dx
         float nrm[3] = {0.f, 0.f, 0.f};

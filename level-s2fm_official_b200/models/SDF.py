@@ -103,42 +103,18 @@ class SDF(nn.Module):
                        depth_range=(0.0, 2.4), max_points=3500000, rad=1.0, iter=0):
         """Bidirectional sphere tracing (models/SDF.py:116-226).  Returns (d_pred [B,M] differentiable w.r.t. the
         field parameters, sdf_last [B*M], sampled_pts [1,*,3] (random eikonal points), finish_mask [B*M,1])."""
-        lib_o, lib_d = ray0.detach().reshape(-1, 3).float().contiguous(), ray_direction.detach().reshape(-1, 3).float().contiguous()
         from .. import _C
-        hits, _ = ops.ray_aabb_raw(_C.get(), lib_o, lib_d, self.center.view(3).tolist(), self.half_size.view(3).tolist())
-        t_near, t_far = hits[:, 0], hits[:, 1]
-        thr = self.sdf_threshold
-        with torch.no_grad():
-            acc_s, acc_e = t_near.clone(), t_far.clone()
-            p_s = lib_o + acc_s[:, None] * lib_d
-            p_e = lib_o + acc_e[:, None] * lib_d
-            both = self.infer_sdf(torch.stack([p_s, p_e]))[..., 0]
-            s_s, s_e = both[0].clone(), both[1].clone()
-            un_s = un_e = None
-            track = []
-            iters = 0
-            while True:
-                s_s = torch.where(s_s.abs() <= thr, torch.zeros_like(s_s), s_s)
-                s_e = torch.where(s_e.abs() <= thr, torch.zeros_like(s_e), s_e)
-                if un_s is None:
-                    un_s, un_e = s_s.abs() > thr, s_e.abs() > thr
-                else:
-                    un_s, un_e = un_s & (s_s.abs() > thr), un_e & (s_e.abs() > thr)
-                if iters == self.iters_max or not bool(un_s.any()):
-                    break
-                iters += 1
-                acc_s = torch.minimum(acc_s + s_s, t_far)
-                acc_e = torch.minimum(acc_e + s_e, t_far)
-                track.append(p_s)
-                p_s = lib_o + acc_s[:, None] * lib_d
-                p_e = lib_o + acc_e[:, None] * lib_d
-                both = self.infer_sdf(torch.stack([p_s, p_e]))[..., 0]
-                s_s = torch.where(un_s, both[0], s_s)
-                s_e = torch.where(un_e, both[1], s_e)
-                un_s, un_e = un_s & (acc_s < acc_e), un_e & (acc_s < acc_e)
-            if not track:
-                track = [p_s]
-            pts_tracks = torch.stack(track, dim=1)                       # [M,K,3]
+        o = ray0.detach().reshape(-1, 3).float().contiguous()
+        d = ray_direction.detach().reshape(-1, 3).float().contiguous()
+        # the whole no-grad march (both fronts, thresholds, crossing test) is one kernel launch; the reference's
+        # per-iteration host synchronisations collapse into ONE read-back of the iteration count K at the end
+        track, cnt, t_near, t_far, acc_hist = ops.sphere_trace_raw(
+            _C.get(), self.field_spec(), self.table().detach(), self.SDF_MLP.theta().detach().contiguous(), o, d,
+            self.sdf_threshold, self.iters_max)
+        done = (cnt == 0).nonzero()
+        n_it = int(done[0, 0]) if done.numel() else self.iters_max          # iterations the reference's loop runs
+        acc_e = acc_hist[n_it]
+        pts_tracks = track[:, :max(n_it, 1)]                                # [M,K,3]; K = 0 keeps the start point
         sdf_tracks = self.infer_sdf(pts_tracks)                          # [M,K,1], with grad
         d_pred = sdf_tracks.sum(dim=-2).view(*ray0.shape[:-1]) + t_near.view(*ray0.shape[:-1])
         d_pred = torch.minimum(d_pred, t_far.view(*d_pred.shape))

@@ -410,3 +410,18 @@ def sample_error_bounded_raw(lib, spec: FieldSpec, table, theta, beta_param, cen
     _call(lib, "sample_error_bounded", lib.dll.ls2fm_sample_error_bounded, f, lib.ptr(beta_param), cfg, lib.ptr(center), lib.ptr(ray),
           r, lib.ptr(ws), lib.ptr(t), lib.ptr(beta_plus), lib.ptr(iters), lib.stream())
     return t, beta_plus, iters
+
+
+def sphere_trace_raw(lib, spec: FieldSpec, table, theta, ray0, ray_dir, sdf_threshold, iters_max):
+    """No-grad march of SDF.sphere_tracing -> (track [M,iters_max,3], n_unfinished [iters_max+1] int32,
+    t_near [M], t_far [M], acc_end [iters_max+1, M])."""
+    m = ray0.numel() // 3
+    dev = ray0.device
+    track = torch.empty(m, iters_max, 3, device=dev)
+    cnt = torch.empty(iters_max + 1, dtype=torch.int32, device=dev)
+    t_near, t_far = torch.empty(m, device=dev), torch.empty(m, device=dev)
+    acc_end = torch.empty(iters_max + 1, m, device=dev)
+    f = spec.c_field(lib, table, theta)
+    _call(lib, "sphere_trace", lib.dll.ls2fm_sphere_trace, f, lib.ptr(ray0), lib.ptr(ray_dir), m, float(sdf_threshold), int(iters_max),
+          lib.ptr(track), lib.ptr(cnt, torch.int32), lib.ptr(t_near), lib.ptr(t_far), lib.ptr(acc_end), lib.stream())
+    return track, cnt, t_near, t_far, acc_end

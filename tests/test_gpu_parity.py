@@ -154,3 +154,7 @@ def test_errors_are_raised(product_lib):
     with pytest.raises(RuntimeError, match="n_samples"):
         ops.composite_forward_raw(product_lib, torch.ones(2, 3, device=DEV), torch.ones(2, 1, device=DEV),
                                   torch.ones(2, 1, device=DEV), None, None, torch.zeros(1, device=DEV), 1.0, (0, 0, 0))
+
+
+def test_fused_sphere_trace_kernel_internals():
+    gc.sphere_trace_internals(DEV)

@@ -94,3 +94,7 @@ def test_golden_error_bounded_sampler_through_kernels():
 @pytest.mark.parametrize("eps,N,std", [(0.002, 16, 0.05), (0.02, 32, 0.1)])
 def test_error_bounded_sampler_hard_cases(eps, N, std):
     gc.sampler_hard_case("cpu", eps, N, std)
+
+
+def test_fused_sphere_trace_kernel_internals():
+    gc.sphere_trace_internals("cpu")
