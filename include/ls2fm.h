@@ -69,6 +69,8 @@ typedef struct {
     float softplus_threshold;  /* 20 */
     float sdf_sign;       /* +1 when opt.data.inside else -1:  sdf = sdf_sign * (y0 / scale_mlp) */
     float scale_mlp;      /* opt.SDF.NN_Init.scale_mlp */
+    const float* tc_image; /* device, nullable: tensor-core operand image of theta (+ radiance) built by ls2fm_field_prepare;
+                              when NULL every forward launch converts the weights itself */
 } ls2fm_field_t;
 
 /* Where the sample points come from. */
@@ -128,6 +130,14 @@ int ls2fm_grid_encode(const ls2fm_field_t* field, const float* u, int64_t m,
 int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64_t m,
                                const float* g_enc, float* d_table, float* d_u, void* stream);
 
+/* ------------------------------------------------------------------ tensor-core operand image
+ * The tcgen05 forward kernel wants the weights as hi/lo TF32 operands in its shared-memory layout (W_l and W_l^T, K-major
+ * core matrices, biases, W_eff).  ls2fm_field_prepare converts theta (+ the radiance block, nullable) ONCE into `image`
+ * (ls2fm_field_image_floats floats); kernels launched with field.tc_image = image copy it with 16-byte loads instead of
+ * re-deriving it per launch (the sampler alone launches the field kernel once per up-sampling round). */
+int64_t ls2fm_field_image_floats(const ls2fm_field_t* field, const ls2fm_radiance_t* rad);
+int ls2fm_field_prepare(const ls2fm_field_t* field, const ls2fm_radiance_t* rad, float* image, void* stream);
+
 /* ------------------------------------------------------------------ fused field evaluation
  * replaces SDF.infer_sdf (+ SDF.gradient) / RadF.Geometry_feat (+ RadF.infer_app when rad != NULL).
  *   out_y   [n, dout]  raw MLP output                                  (nullable)
@@ -137,6 +147,11 @@ int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64
 int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts,
                         const ls2fm_radiance_t* rad,
                         float* out_y, float* out_sdf, float* out_nrm, float* out_rgb, void* stream);
+/* Same contract, MLP on the fp32 SIMT pipes instead of tcgen05 (3xTF32) tensor cores: the cross-check of the
+ * tensor-core kernel and the path for networks whose weight operands do not fit in shared memory. */
+int ls2fm_field_forward_simt(const ls2fm_field_t* field, const ls2fm_points_t* pts,
+                             const ls2fm_radiance_t* rad,
+                             float* out_y, float* out_sdf, float* out_nrm, float* out_rgb, void* stream);
 
 /* backward of ls2fm_field_forward.  Upstream gradients (all nullable): g_y [n,dout], g_sdf [n],
  * g_nrm [n,3], g_rgb [n,3].  saved_nrm/saved_rgb: forward outputs (required when rad != NULL).

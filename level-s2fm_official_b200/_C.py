@@ -39,7 +39,7 @@ class Field(C.Structure):
                 ("levels", Level * MAX_LEVELS), ("bound_min", C.c_float * 3), ("bound_max", C.c_float * 3),
                 ("rescale", C.c_float), ("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)),
                 ("softplus_beta", C.c_float), ("softplus_threshold", C.c_float),
-                ("sdf_sign", C.c_float), ("scale_mlp", C.c_float)]
+                ("sdf_sign", C.c_float), ("scale_mlp", C.c_float), ("tc_image", C.c_void_p)]
 
 
 class Points(C.Structure):
@@ -72,7 +72,10 @@ SIGNATURES = {
     "ls2fm_ray_aabb": (C.c_int, [_VP, _VP, C.c_int64, _F3, _F3, _VP, _VP, _VP]),
     "ls2fm_grid_encode": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP]),
     "ls2fm_grid_encode_backward": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    "ls2fm_field_image_floats": (C.c_int64, [C.POINTER(Field), C.POINTER(Radiance)]),
+    "ls2fm_field_prepare": (C.c_int, [C.POINTER(Field), C.POINTER(Radiance), _VP, _VP]),
     "ls2fm_field_forward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),
+    "ls2fm_field_forward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),
     "ls2fm_composite_forward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 5),
     "ls2fm_composite_backward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 9),

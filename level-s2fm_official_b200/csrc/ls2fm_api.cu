@@ -6,6 +6,7 @@
 #include <string>
 
 #include "ls2fm_field.cuh"
+#include "ls2fm_field_tc.cuh"
 #include "ls2fm_render.cuh"
 #include "ls2fm_sampler.cuh"
 #include "ls2fm_trace.cuh"
@@ -190,12 +191,37 @@ int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64
     return ls_check_launch("grid_encode_backward");
 }
 
-int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, float* out_y,
-                        float* out_sdf, float* out_nrm, float* out_rgb, void* stream) {
+int64_t ls2fm_field_image_floats(const ls2fm_field_t* field, const ls2fm_radiance_t* rad) {
+    if (!field || field->n_layers < 2 || field->n_layers > LS2FM_MAX_LAYERS) return -1;
+    return (int64_t)ls_plan_tc(*field, rad ? rad->in_dim : 0).misc;
+}
+
+int ls2fm_field_prepare(const ls2fm_field_t* field, const ls2fm_radiance_t* rad, float* image, void* stream) {
+    if (ls_check_field(field)) return 1;
+    if (!image) return ls_fail("field_prepare: image is NULL");
+    if (rad && (!rad->w_eff || !rad->b_eff)) return ls_fail("field_prepare: radiance.w_eff / b_eff is NULL");
+    LsFieldArgs a;
+    ls2fm_points_t pts;
+    memset(&pts, 0, sizeof(pts));
+    ls_fill_args(a, field, &pts, rad);
+    a.net = ls_plan_net(*field, rad ? rad->in_dim : 0, 1, false);
+    const LsTcNet net = ls_plan_tc(*field, rad ? rad->in_dim : 0);
+    LS_LAUNCH(ls_field_prepare_kernel, 32, 256, 0, stream, a, net, image);
+    return ls_check_launch("field_prepare");
+}
+
+static int ls_field_forward_checks(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, float* out_rgb) {
     if (ls_check_field(field) || ls_check_points(pts)) return 1;
     if (pts->n == 0) return 0;
     if (rad && ls_check_rad(rad, field, pts)) return 1;
     if (out_rgb && !rad) return ls_fail("field_forward: out_rgb needs the radiance block");
+    return 0;
+}
+
+int ls2fm_field_forward_simt(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, float* out_y,
+                             float* out_sdf, float* out_nrm, float* out_rgb, void* stream) {
+    if (ls_field_forward_checks(field, pts, rad, out_rgb)) return 1;
+    if (pts->n == 0) return 0;
     LsFieldArgs a;
     ls_fill_args(a, field, pts, rad);
     a.out_y = out_y; a.out_sdf = out_sdf; a.out_nrm = out_nrm; a.out_rgb = out_rgb;
@@ -212,6 +238,25 @@ int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, c
     int64_t grid = (n_tiles + nw - 1) / nw;
     if (grid > ls_sm_count()) grid = ls_sm_count();
     LS_LAUNCH(ls_field_forward_kernel, (unsigned)grid, nw * 32, smem, stream, a);
+    return ls_check_launch("field_forward_simt");
+}
+
+int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, float* out_y,
+                        float* out_sdf, float* out_nrm, float* out_rgb, void* stream) {
+    if (ls_field_forward_checks(field, pts, rad, out_rgb)) return 1;
+    if (pts->n == 0) return 0;
+    LsFieldArgs a;
+    ls_fill_args(a, field, pts, rad);
+    a.out_y = out_y; a.out_sdf = out_sdf; a.out_nrm = out_nrm; a.out_rgb = out_rgb;
+    a.net = ls_plan_net(*field, rad ? rad->in_dim : 0, 1, false);        // theta offsets
+    const LsTcNet net = ls_plan_tc(*field, rad ? rad->in_dim : 0);
+    const int smem = net.total * (int)sizeof(float);
+    if (smem > ls_max_smem() || (field->n_levels & 3))     // operands too large / level groups not chunk-aligned: SIMT kernel
+        return ls2fm_field_forward_simt(field, pts, rad, out_y, out_sdf, out_nrm, out_rgb, stream);
+    if (ls_opt_in_smem(ls_field_forward_tc_kernel, smem)) return 1;
+    const int64_t n_tiles = (pts->n + LS_TC_M - 1) / LS_TC_M;
+    int64_t grid = n_tiles < ls_sm_count() ? n_tiles : ls_sm_count();
+    LS_LAUNCH(ls_field_forward_tc_kernel, (unsigned)grid, LS_TC_THREADS, smem, stream, a, net);
     return ls_check_launch("field_forward");
 }
 

@@ -136,7 +136,7 @@ LS_DEV void ls_prod_rev(const float* Wt, int pitch, int n_rows, int n_j, const f
     }
     const float* p0 = z0 + sg * R * 4;
     const float* p1 = z1 + sg * R * 4;
-#pragma unroll 2
+#pragma unroll 1
     for (int j = 0; j < n_j; j += 4) {
         float4 w[NQ];
 #pragma unroll
@@ -303,6 +303,7 @@ LS_DEV void ls_encode_tile(const LsFieldArgs& a, float* E, const float x[3], int
 // grid: persistent, blockDim = 32 * n_warps; every warp walks tiles independently.
 __global__ void __launch_bounds__(512, 1) ls_field_forward_kernel(const LsFieldArgs a) {
     LS_DYN_SMEM(smem);
+    if (ls_n_samples(a.p) == 0) return;
     ls_stage_weights(a, smem);
     __syncthreads();
 
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
             ls_el(P, LS_H, o, s8) = v;
         }
         // ------------------------------------------------ B2: gather, e and (TAN) edot = Je nbar
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < 4; ++r) {
             const int l = g + 4 * r;
             if (l < L) {
@@ -710,6 +711,7 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                 const int c = tid < 3 * in_dim ? tid / in_dim : tid - 3 * in_dim;
                 const int idx = tid < 3 * in_dim ? tid - c * in_dim : -1;
                 float acc = 0.f;
+#pragma unroll 1
                 for (int w = 0; w < LS_BW_WARPS; ++w) {
                     const float* wP = WB + w * WSTR + oP;
                     const float* wPd = WB + w * WSTR + oPd;
@@ -752,9 +754,10 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                 for (int q = 0; q < 4; ++q) { int r = bj + 16 * q; rz[q] = r < n_zrows ? r : n_zrows - 1; }
                 float bsum = 0.f;
                 const int brow = tid < n_zrows ? tid : n_zrows - 1;
+#pragma unroll 1
                 for (int w = 0; w < LS_BW_WARPS; ++w) {
                     const float* base = WB + w * WSTR;
-#pragma unroll
+#pragma unroll 1
                     for (int h2 = 0; h2 < 2; ++h2) {
                         float4 iv[4], zv[4];
 #pragma unroll
@@ -831,7 +834,7 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
 
         // ------------------------------------------------ B6: hash-table gradient scatter
         if (a.d_table && valid) {
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < 4; ++r) {
                 const int l = g + 4 * r;
                 if (l < L) {

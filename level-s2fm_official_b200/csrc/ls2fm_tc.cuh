@@ -1,0 +1,170 @@
+// ls2fm_tc.cuh -- thin wrappers over the sm_100a tensor-core path (tcgen05 + TMEM) used by the MLP core.
+//
+// Model (validated on B200 by tools/probe/tc_probe*.cu before any kernel was built on it):
+//   * D[128 x N] (fp32) lives in TMEM: lane = row (= the sample owned by thread `lane`), column = output feature.
+//   * A[128 x K] comes from TMEM as well (lane = row, one 32-bit column per K element) -- the epilogue threads write the
+//     next layer's input there with tcgen05.st, so activations never touch shared memory in the forward kernel.
+//   * B[N x K] comes from shared memory, K-major, no swizzle: 8-row x 16-byte core matrices,
+//       addr(n, k) = (k/4) * (N*16) + (n/8)*128 + (n%8)*16 + (k%4)*4     (LBO = N*16 bytes, SBO = 128 bytes).
+//     (MN-major / transposed reads of tf32 operands returned zeros in every descriptor variant probed, so transposed
+//     products use an explicitly transposed copy of the weights instead.)
+//   * kind::tf32 keeps 10 mantissa bits; fp32-level accuracy comes from the 3xTF32 split
+//       a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,   x_hi = tf32(x) (round to nearest), x_lo = x - x_hi,
+//     measured 5e-7 relative on 64-long dot products (tools/probe/tc_probe.cu) vs 3e-4 for a single pass.
+//   * one thread issues the MMAs; completion is signalled through an mbarrier (tcgen05.commit).
+//
+// Under LS_HOSTSIM (tests/hostsim) the same entry points are emulated on the CPU with the same data layouts
+// (TMEM = a per-block [128][512] array, operands truncated to tf32), so the kernels' indexing is testable without a GPU.
+#pragma once
+
+#include "ls2fm_common.cuh"
+
+constexpr int LS_TC_M = 128;        // rows (samples) per tile = threads per CTA of the tensor-core kernels
+constexpr int LS_TMEM_COLS = 512;
+
+// byte offset of element (row n, k) of a K-major no-swizzle operand with `rows` rows
+LS_DEV int ls_op_off(int n, int k, int rows) { return (k >> 2) * (rows * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4; }
+
+#if defined(LS_HOSTSIM)
+// ------------------------------------------------------------------------------------------------ CPU emulation
+struct LsTmemSim { float v[LS_TC_M][LS_TMEM_COLS]; };
+inline LsTmemSim& ls_tmem_sim() { static LsTmemSim t; return t; }
+inline float ls_tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; }
+inline float ls_tf32_round(float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    u += 0x00001000u;               // round to nearest (ties away), like cvt.rna.tf32.f32
+    u &= 0xFFFFE000u;
+    float r; memcpy(&r, &u, 4); return r;
+}
+struct LsTcBar { int arrived; };
+LS_DEV uint32_t ls_tc_alloc(uint32_t*) { __syncthreads(); return 0; }
+LS_DEV void ls_tc_dealloc(uint32_t) { __syncthreads(); }
+LS_DEV void ls_tc_bar_init(LsTcBar* b) { if (threadIdx.x == 0) b->arrived = 0; __syncthreads(); }
+LS_DEV int ls_tc_row() { return (int)(((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31)); }
+LS_DEV void ls_tmem_ld(uint32_t, int col, float* v, int n) { for (int i = 0; i < n; ++i) v[i] = ls_tmem_sim().v[ls_tc_row()][col + i]; }
+LS_DEV void ls_tmem_st(uint32_t, int col, const float* v, int n) { for (int i = 0; i < n; ++i) ls_tmem_sim().v[ls_tc_row()][col + i] = v[i]; }
+LS_DEV void ls_tc_sync_before_mma() { __syncthreads(); }
+// D[:, d_col + n] (+)= sum_k A[:, a_col + k] * B[n][k]   for n < N, k < K  (called by ONE thread)
+LS_DEV void ls_tc_mma(uint32_t, int d_col, int a_col, const float* B, int N, int K, bool accumulate) {
+    LsTmemSim& t = ls_tmem_sim();
+    for (int m = 0; m < LS_TC_M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float acc = accumulate ? t.v[m][d_col + n] : 0.f;
+            for (int k = 0; k < K; ++k)
+                acc += ls_tf32_trunc(t.v[m][a_col + k]) * ls_tf32_trunc(*(const float*)((const char*)B + ls_op_off(n, k, N)));
+            t.v[m][d_col + n] = acc;
+        }
+}
+LS_DEV void ls_tc_commit(LsTcBar* b) { b->arrived += 1; }
+LS_DEV void ls_tc_wait(LsTcBar*, uint32_t& phase) { __syncthreads(); phase ^= 1; }
+LS_DEV void ls_split_tf32(float v, float& hi, float& lo) { hi = ls_tf32_round(v); lo = v - hi; }
+LS_DEV void ls_fence_smem_to_async() {}
+#else
+// ------------------------------------------------------------------------------------------------ sm_100a
+struct LsTcBar { unsigned long long v; };
+LS_DEV uint32_t ls_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// warp 0 allocates all 512 columns; every thread returns the base address
+LS_DEV uint32_t ls_tc_alloc(uint32_t* slot) {
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(ls_smem_u32(slot)), "n"(LS_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    return *slot;
+}
+LS_DEV void ls_tc_dealloc(uint32_t tmem) {
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "n"(LS_TMEM_COLS));
+}
+LS_DEV void ls_tc_bar_init(LsTcBar* b) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(ls_smem_u32(b)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n");
+    }
+    __syncthreads();
+}
+// this thread's TMEM lane: a warp may only touch the lane quarter (warp_id % 4); warps w, w+4, w+8, ... share a quarter
+LS_DEV int ls_tc_row() { return (int)(((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31)); }
+LS_DEV uint32_t ls_tmem_lane_addr(uint32_t tmem, int col) { return tmem + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16) + (uint32_t)col; }
+LS_DEV void ls_tmem_ld16(uint32_t addr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+LS_DEV void ls_tmem_ld8(uint32_t addr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+LS_DEV void ls_tmem_st8(uint32_t addr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+                 :: "r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                    "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+// n must be a multiple of 8 (compile-time unrolled by the callers)
+LS_DEV void ls_tmem_ld(uint32_t tmem, int col, float* v, int n) {
+    int i = 0;
+    for (; i + 16 <= n; i += 16) ls_tmem_ld16(ls_tmem_lane_addr(tmem, col + i), v + i);
+    for (; i + 8 <= n; i += 8) ls_tmem_ld8(ls_tmem_lane_addr(tmem, col + i), v + i);
+}
+LS_DEV void ls_tmem_st(uint32_t tmem, int col, const float* v, int n) {
+    for (int i = 0; i + 8 <= n; i += 8) ls_tmem_st8(ls_tmem_lane_addr(tmem, col + i), v + i);
+}
+// all threads: my TMEM stores are done and ordered before the barrier; after it one thread may issue MMAs that read them
+LS_DEV void ls_tc_sync_before_mma() {
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+}
+LS_DEV uint64_t ls_tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46);
+}
+// D[:, d_col + n] (+)= sum_k A[:, a_col + k] * B[n][k]; A from TMEM, B K-major no-swizzle in smem; N % 16 == 0, K % 8 == 0
+LS_DEV void ls_tc_mma(uint32_t tmem, int d_col, int a_col, const float* B, int N, int K, bool accumulate) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(LS_TC_M >> 4) << 24);
+    const uint32_t b0 = ls_smem_u32(B);
+    for (int kb = 0; kb < K / 8; ++kb) {
+        const uint64_t bdesc = ls_tc_desc(b0 + kb * 2 * (N * 16), N * 16, 128);
+        const uint32_t acc = (accumulate || kb > 0) ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+                     :: "r"(tmem + (uint32_t)d_col), "r"(tmem + (uint32_t)(a_col + kb * 8)), "l"(bdesc), "r"(idesc), "r"(acc));
+    }
+}
+LS_DEV void ls_tc_commit(LsTcBar* b) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(ls_smem_u32(b)) : "memory");
+}
+LS_DEV void ls_tc_wait(LsTcBar* b, uint32_t& phase) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(ls_smem_u32(b)), "r"(phase) : "memory");
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+}
+LS_DEV void ls_split_tf32(float v, float& hi, float& lo) {
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    hi = __uint_as_float(hb);
+    lo = v - hi;
+}
+LS_DEV void ls_fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+#endif
+
+// 3xTF32 product by the issuing thread: D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi (small terms first)
+LS_DEV void ls_tc_mma_x3(uint32_t tmem, int d_col, int a_hi_col, int a_lo_col, const float* b_hi, const float* b_lo, int N, int K) {
+    ls_tc_mma(tmem, d_col, a_lo_col, b_hi, N, K, false);
+    ls_tc_mma(tmem, d_col, a_hi_col, b_lo, N, K, true);
+    ls_tc_mma(tmem, d_col, a_hi_col, b_hi, N, K, true);
+}

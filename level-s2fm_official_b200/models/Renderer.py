@@ -35,14 +35,27 @@ class Renderer:
         i = 0.5 + torch.arange(n, device=min_d.device)[None, None, :, None].float()
         return i / n * (max_d[..., None, :] - min_d[..., None, :]) + min_d[..., None, :]
 
-    def volsdf_sampling(self, opt, center, ray, SDF_Field, det=True):
+    def _prepare(self, SDF_Field, Rad_Field=None):
+        """Effective weights (weight-norm, composed radiance map) and their tensor-core operand image, built once per
+        call and shared by every launch that evaluates the same parameters (sampler rounds + render forward)."""
+        lib = _C.get()
+        theta = SDF_Field.SDF_MLP.theta()
+        w_eff = b_eff = rad = None
+        if Rad_Field is not None:
+            w_eff, b_eff = Rad_Field.Rad_dec.effective_affine()
+            rad = ops._rad(lib, Rad_Field.rad_spec(), w_eff.detach(), b_eff.detach(), None)
+        image = ops.field_prepare_raw(lib, SDF_Field.field_spec(), SDF_Field.table().detach(), theta.detach().contiguous(), rad)
+        return {"theta": theta, "w_eff": w_eff, "b_eff": b_eff, "image": image}
+
+    def volsdf_sampling(self, opt, center, ray, SDF_Field, det=True, prepared=None):
         """Depth samples [B,R,N] (returned three times like the reference's default branch)."""
         B, R = center.shape[:2]
         c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
         v = opt.SDF.VolSDF
         if v.volsdf_sampling == True:   # noqa: E712
             from .. import sampler
-            t, beta_plus, iters = sampler.error_bounded(self, opt, c2, r2, SDF_Field)
+            prepared = prepared or self._prepare(SDF_Field)
+            t, beta_plus, iters = sampler.error_bounded(self, opt, c2, r2, SDF_Field, prepared)
             return t.view(B, R, -1), beta_plus.view(B, R), iters.view(B, R)
         t, _ = ops.sample_uniform_raw(_C.get(), c2, r2, int(v.sample_intvs), [float(x) for x in opt.data.bound_min],
                                       [float(x) for x in opt.data.bound_max])
@@ -51,11 +64,13 @@ class Renderer:
 
     # ------------------------------------------------------------------ the hot path
     def forward(self, opt, center, ray, SDF_Field, Rad_Field):
-        t, _, _ = self.volsdf_sampling(opt, center, ray, SDF_Field=SDF_Field)
-        return self.render_with_depths(opt, center, ray, t, SDF_Field, Rad_Field)
+        prepared = self._prepare(SDF_Field, Rad_Field)
+        t, _, _ = self.volsdf_sampling(opt, center, ray, SDF_Field=SDF_Field, prepared=prepared)
+        return self.render_with_depths(opt, center, ray, t, SDF_Field, Rad_Field, prepared=prepared)
 
-    def render_with_depths(self, opt, center, ray, t, SDF_Field, Rad_Field):
+    def render_with_depths(self, opt, center, ray, t, SDF_Field, Rad_Field, prepared=None):
         """Everything of Renderer.forward after the depth sampler (models/Renderer.py:57-116) for given depths t [B,R,N]."""
+        prepared = prepared or self._prepare(SDF_Field, Rad_Field)
         B, R = center.shape[:2]
         N = t.shape[-1]
         c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
@@ -65,10 +80,9 @@ class Renderer:
             _, geo2, _, _ = ops.FieldEval.apply(Rad_Field.field_spec(), None, Rad_Field.embed_fn.embedder_obj.params,
                                                 Rad_Field.Geo_enc.theta(), None, None, None, None, c2, r2, t2, 0, None,
                                                 True, False)
-        w_eff, b_eff = Rad_Field.Rad_dec.effective_affine()
         sdf, _, nrm, rgbs = ops.FieldEval.apply(SDF_Field.field_spec(), Rad_Field.rad_spec(), SDF_Field.table(),
-                                                SDF_Field.SDF_MLP.theta(), w_eff, b_eff, geo2, None, c2, r2, t2, 0, None,
-                                                False, True)
+                                                prepared["theta"], prepared["w_eff"], prepared["b_eff"], geo2, None, c2, r2, t2,
+                                                0, None, False, True, prepared["image"])
         ray_in = ray.reshape(-1, 3).float() if ray.requires_grad else r2
         rgb, depth, normal, _ = ops.Composite.apply(ray_in, t2, sdf.view(B * R, N), rgbs.view(B * R, N, 3),
                                                     nrm.view(B * R, N, 3), SDF_Field.beta, float(SDF_Field.beta_speed),

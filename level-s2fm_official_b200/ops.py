@@ -68,10 +68,11 @@ class FieldSpec:
     def theta_size(self) -> int:
         return sum(self.dims[l] * self.dims[l + 1] + self.dims[l + 1] for l in range(self.n_layers))
 
-    def c_field(self, lib: _C.Lib, table: torch.Tensor, theta: Optional[torch.Tensor]) -> _C.Field:
+    def c_field(self, lib: _C.Lib, table: torch.Tensor, theta: Optional[torch.Tensor], image: Optional[torch.Tensor] = None) -> _C.Field:
         f = _C.Field()
         f.table = lib.ptr(table)
         f.theta = lib.ptr(theta) if theta is not None else None
+        f.tc_image = lib.ptr(image) if image is not None else None
         f.n_levels = self.grid.n_levels
         for i, lv in enumerate(self.grid.levels):
             f.levels[i] = lv
@@ -198,14 +199,24 @@ def _rad(lib: _C.Lib, rs: RadSpec, w_eff, b_eff, geo2):
     return r
 
 
+def field_prepare_raw(lib, spec: FieldSpec, table, theta, rad: Optional[_C.Radiance]):
+    """theta (+ W_eff) -> tensor-core operand image (hi/lo TF32, kernel shared-memory layout); reuse it for every launch
+    that evaluates the same parameters (sampler rounds, render forward, sphere tracing)."""
+    f = spec.c_field(lib, table, theta)
+    n = int(lib.dll.ls2fm_field_image_floats(f, rad))
+    image = torch.empty(n, device=table.device)
+    _call(lib, "field_prepare", lib.dll.ls2fm_field_prepare, f, rad, lib.ptr(image), lib.stream())
+    return image
+
+
 def field_forward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: Optional[_C.Radiance],
-                      want_y=False, want_sdf=True, want_nrm=False, want_rgb=False):
+                      want_y=False, want_sdf=True, want_nrm=False, want_rgb=False, image=None):
     n, dev = int(pts.n), table.device
     y = torch.empty(n, spec.dout, device=dev) if want_y else None
     sdf = torch.empty(n, device=dev) if want_sdf else None
     nrm = torch.empty(n, 3, device=dev) if want_nrm else None
     rgb = torch.empty(n, 3, device=dev) if want_rgb else None
-    f = spec.c_field(lib, table, theta)
+    f = spec.c_field(lib, table, theta, image)
     _call(lib, "field_forward", lib.dll.ls2fm_field_forward, f, pts, rad, lib.ptr(y), lib.ptr(sdf), lib.ptr(nrm), lib.ptr(rgb), lib.stream())
     return y, sdf, nrm, rgb
 
@@ -298,7 +309,7 @@ class FieldEval(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, rad_spec, table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, t_offset, n_per_ray,
-                want_y, want_nrm):
+                want_y, want_nrm, image=None):
         lib = _C.get()
         table, theta = table.detach().contiguous(), theta.detach().contiguous()
         xyz, center, ray, t = _c(xyz), _c(center), _c(ray), _c(t)
@@ -309,7 +320,7 @@ class FieldEval(torch.autograd.Function):
         pts = _points(lib, xyz, center, ray, t, t_offset, n_per_ray)
         rad = _rad(lib, rad_spec, w_eff, b_eff, geo2) if with_rad else None
         y, sdf, nrm, rgb = field_forward_raw(lib, spec, table, theta, pts, rad, want_y=want_y, want_sdf=True,
-                                             want_nrm=want_nrm or with_rad, want_rgb=with_rad)
+                                             want_nrm=want_nrm or with_rad, want_rgb=with_rad, image=image)
         ctx.spec, ctx.rad_spec = spec, rad_spec
         ctx.pt_args = (t_offset, n_per_ray)
         ctx.with_rad, ctx.want_y, ctx.want_nrm = with_rad, want_y, want_nrm
@@ -339,7 +350,7 @@ class FieldEval(torch.autograd.Function):
         d_geo2 = torch.empty_like(geo2) if (with_rad and geo2 is not None) else None
         field_backward_raw(lib, spec, table, theta, pts, rad, g_y, g_sdf, g_nrm, g_rgb, s_nrm, s_rgb,
                            d_table, d_theta, d_w, d_b, d_geo2)
-        return (None, None, d_table, d_theta, d_w, d_b, d_geo2, None, None, None, None, None, None, None, None)
+        return (None, None, d_table, d_theta, d_w, d_b, d_geo2, None, None, None, None, None, None, None, None, None)
 
 
 class Composite(torch.autograd.Function):
@@ -394,7 +405,7 @@ class GridEncode(torch.autograd.Function):
 
 
 def sample_error_bounded_raw(lib, spec: FieldSpec, table, theta, beta_param, center, ray, n_samples, n_final,
-                             max_upsample_iter, max_bisection_itr, eps, beta_speed):
+                             max_upsample_iter, max_bisection_itr, eps, beta_speed, image=None):
     """Renderer.volsdf_sampling's error-bounded branch -> (t [R, N+Nf], beta_plus [R], iters [R])."""
     r = center.numel() // 3
     dev = center.device
@@ -406,7 +417,7 @@ def sample_error_bounded_raw(lib, spec: FieldSpec, table, theta, beta_param, cen
     t = torch.empty(r, n_samples + n_final, device=dev)
     beta_plus = torch.empty(r, device=dev)
     iters = torch.empty(r, device=dev)
-    f = spec.c_field(lib, table, theta)
+    f = spec.c_field(lib, table, theta, image)
     _call(lib, "sample_error_bounded", lib.dll.ls2fm_sample_error_bounded, f, lib.ptr(beta_param), cfg, lib.ptr(center), lib.ptr(ray),
           r, lib.ptr(ws), lib.ptr(t), lib.ptr(beta_plus), lib.ptr(iters), lib.stream())
     return t, beta_plus, iters
