@@ -154,10 +154,11 @@ def run_reference(args):
         times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     val = n_rays / (ms / 1e3)
-    line = {"impl": "reference", "metric": "rendered rays/sec (fwd+bwd)", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": "rendered rays/sec (fwd+bwd, 4096-ray batch)", "value": val, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[args.workload], "sample": f"each step = {n_rays} rays of that workload"},
+            "config": {"workload": WORKLOAD_DESC[args.workload], "rays_per_gpu": RAYS_PER_GPU, "regime": "init",
+                       "sample": f"each step = {n_rays} rays of that workload (CPU, bounded)"},
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} timed fwd+bwd steps of {n_rays} rays (oracle/port.py: the reference's algorithm "
                                        "restated in eager PyTorch on the host cores; tcnn/vren are not installable here)"},
@@ -293,8 +294,12 @@ def main():
     #   field_forward : gather S*G + 28 B/sample of outputs
     alg = {"field_backward": S * (2 * G + 52), "field_forward": S * (G + 28)}.get(dom, S * G)
     achieved = alg / (durs[dom] * 1e-3) / 1e9
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    if os.path.exists(tr_path) and args.workload == "c2":
+        traffic = json.load(open(tr_path)).get(dom)          # dram__bytes_read + dram__bytes_write per launch (ncu --set full)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg, "launch_ms": durs[dom],
                 "kernel_ms_per_step": per_step_kernel_ms}
 

@@ -283,13 +283,15 @@ int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, 
     if (smem > ls_max_smem()) return ls_fail("field_backward: network does not fit in shared memory");
     const int64_t n_ct = (pts->n + LS_WS * LS_BW_WARPS - 1) / (LS_WS * LS_BW_WARPS);
     int64_t grid = n_ct < ls_sm_count() ? n_ct : ls_sm_count();
-    if (tan) {
-        if (ls_opt_in_smem(ls_field_backward_kernel<true>, smem)) return 1;
-        LS_LAUNCH(ls_field_backward_kernel<true>, (unsigned)grid, LS_BW_THREADS, smem, stream, a);
-    } else {
-        if (ls_opt_in_smem(ls_field_backward_kernel<false>, smem)) return 1;
-        LS_LAUNCH(ls_field_backward_kernel<false>, (unsigned)grid, LS_BW_THREADS, smem, stream, a);
-    }
+#define LS_BW_LAUNCH(TANV, KV)                                                                          \
+    do {                                                                                                \
+        if (ls_opt_in_smem(ls_field_backward_kernel<TANV, KV>, smem)) return 1;                         \
+        LS_LAUNCH((ls_field_backward_kernel<TANV, KV>), (unsigned)grid, LS_BW_THREADS, smem, stream, a); \
+    } while (0)
+    const int KL = field->n_layers;
+    if (tan) { if (KL == 2) LS_BW_LAUNCH(true, 2); else if (KL == 3) LS_BW_LAUNCH(true, 3); else LS_BW_LAUNCH(true, 4); }
+    else { if (KL == 2) LS_BW_LAUNCH(false, 2); else if (KL == 3) LS_BW_LAUNCH(false, 3); else LS_BW_LAUNCH(false, 4); }
+#undef LS_BW_LAUNCH
     return ls_check_launch("field_backward");
 }
 

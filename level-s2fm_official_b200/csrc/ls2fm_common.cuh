@@ -85,7 +85,10 @@ LS_DEV uint32_t ls_corner_index(uint32_t resolution, uint32_t size, uint32_t has
         // dense level: all three strides fit (that is what hashed == 0 means); uint32 wrap as in tcnn
         index = q0 + q1 * resolution + q2 * resolution * resolution;
     }
-    return index % size;
+    // tcnn: index % hashmap_size.  Hashed levels have power-of-two sizes (mask); dense levels are in range for every
+    // point inside the box, so the (exact) modulo only runs for out-of-range coordinates.
+    if (hashed && (size & (size - 1)) == 0) return index & (size - 1);
+    return index < size ? index : index % size;
 }
 
 // world -> unit cube exactly as models/base.py:35: (x - bmin) / (bmax - bmin)

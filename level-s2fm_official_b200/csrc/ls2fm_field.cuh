@@ -502,14 +502,14 @@ constexpr int LS_BW_WARPS = 8;
 constexpr int LS_BW_THREADS = 32 * LS_BW_WARPS;
 constexpr int LS_IN_ROW0 = LS_OROWS;      // rows of the P|Pd area used for (pbar[3], in[...]) during the W_eff phase
 
-template <bool TAN>
+template <bool TAN, int K>
 __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(const LsFieldArgs a) {
     LS_DYN_SMEM(smem);
     ls_stage_weights(a, smem);
     __syncthreads();
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = a.f.n_layers, L = a.f.n_levels;
+    const int L = a.f.n_levels;
     const int din0 = a.f.dims[0], dout = a.f.dims[K];
     const int hid = K - 1;
     const float sp_beta = a.f.softplus_beta, sp_thr = a.f.softplus_threshold;
@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                         else {
                             const float e = expf(bz);
                             av[s] = log1pf(e) / sp_beta;
-                            dv[s] = accd[q][s] * (e / (e + 1.f));
+                            if (TAN) dv[s] = accd[q][s] * __fdividef(e, e + 1.f);
                         }
                     }
                     ls_st4(ls_row(out, LS_H, sg, 4 * og + q), make_float4(av[0], av[1], av[2], av[3]));
@@ -759,26 +759,28 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                     const float* base = WB + w * WSTR;
 #pragma unroll 1
                     for (int h2 = 0; h2 < 2; ++h2) {
+                        // compile-time pruning: layer 0 has <= 36 input rows (p < 3), the output layer <= 20 columns (q < 2)
+                        const int PM = (l == 0) ? 3 : 4, QM = (l == K - 1) ? 2 : 4;   // constants once the layer loop is unrolled
                         float4 iv[4], zv[4];
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) iv[p] = ls_ld4(ls_row(base + o_in, R_in, h2, rin[p]));
+                        for (int p = 0; p < 4; ++p) if (p < PM) iv[p] = ls_ld4(ls_row(base + o_in, R_in, h2, rin[p]));
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) zv[q] = ls_ld4(ls_row(base + o_z, LS_H, h2, rz[q]));
+                        for (int q = 0; q < 4; ++q) if (q < QM) zv[q] = ls_ld4(ls_row(base + o_z, LS_H, h2, rz[q]));
 #pragma unroll
                         for (int p = 0; p < 4; ++p)
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                wacc[l][p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wacc[l][p][q]))));
+                                if (p < PM && q < QM) wacc[l][p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wacc[l][p][q]))));
                         if (TAN) {
 #pragma unroll
-                            for (int p = 0; p < 4; ++p) iv[p] = ls_ld4(ls_row(base + o_ind, R_in, h2, rin[p]));
+                            for (int p = 0; p < 4; ++p) if (p < PM) iv[p] = ls_ld4(ls_row(base + o_ind, R_in, h2, rin[p]));
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) zv[q] = ls_ld4(ls_row(base + o_zd, LS_H, h2, rz[q]));
+                            for (int q = 0; q < 4; ++q) if (q < QM) zv[q] = ls_ld4(ls_row(base + o_zd, LS_H, h2, rz[q]));
 #pragma unroll
                             for (int p = 0; p < 4; ++p)
 #pragma unroll
                                 for (int q = 0; q < 4; ++q)
-                                    wacc[l][p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wacc[l][p][q]))));
+                                    if (p < PM && q < QM) wacc[l][p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wacc[l][p][q]))));
                         }
                         const float4 bz = ls_ld4(ls_row(base + o_z, LS_H, h2, brow));
                         bsum += bz.x + bz.y + bz.z + bz.w;

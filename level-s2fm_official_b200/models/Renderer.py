@@ -93,6 +93,48 @@ class Renderer:
     render_rays = forward    # north-star alias
 
     # ------------------------------------------------------------------ API-compatible pieces
+    # The reference exposes its building blocks as methods; the fused kernels do not call them (the density, the
+    # compositing, the error bound and the inverse-CDF sampling all live inside the sampler / compositing kernels), but
+    # they stay callable with the reference's signatures and semantics for callers that use them on their own tensors.
     def sdf_to_sigma(self, sdf, alpha, beta):
+        """Laplace-CDF density (models/Renderer.py:164-167)."""
         e = 0.5 * torch.exp(-torch.abs(sdf) / beta)
         return alpha * torch.where(sdf >= 0, e, 1 - e)
+
+    def composite(self, ray, rgb_samples, density_samples, depth_samples):
+        """(models/Renderer.py:33-49)  ray [B,R,3], rgb [B,R,N,3], density [B,R,N], depth [B,R,N,1] -> rgb [B,R,3], prob [B,R,N-1,1]."""
+        ray_length = ray.norm(dim=-1, keepdim=True)
+        dist = (depth_samples[..., 1:, 0] - depth_samples[..., :-1, 0]) * ray_length
+        sd = density_samples[..., :-1] * dist
+        alpha = 1 - torch.exp(-sd)
+        T = torch.exp(-torch.cat([torch.zeros_like(sd[..., :1]), sd], dim=2).cumsum(dim=2))[..., :-1]
+        prob = (T * alpha)[..., None]
+        return (rgb_samples[..., :-1, :] * prob).sum(dim=2), prob
+
+    def error_bound(self, d_vals, sdf, alpha, beta):
+        """VolSDF opacity error bound per interval (models/Renderer.py:330-360): [..., M] -> [..., M-1]."""
+        sigma = self.sdf_to_sigma(sdf, alpha, beta)
+        delta = d_vals[..., 1:] - d_vals[..., :-1]
+        R = torch.cat([torch.zeros_like(sdf[..., :1]), torch.cumsum(sigma[..., :-1] * delta, dim=-1)], dim=-1)[..., :-1]
+        d_star = torch.clamp_min(0.5 * (sdf.abs()[..., :-1] + sdf.abs()[..., 1:] - delta), 0.0)
+        E = torch.cumsum(alpha / (4 * beta) * delta ** 2 * torch.exp(-d_star / beta), dim=-1)
+        bound = torch.exp(-R) * (torch.exp(E) - 1.0)
+        return torch.where(torch.isnan(bound), torch.full_like(bound, float("inf")), bound)
+
+    def sample_pdf(self, bins, weights, N_importance, det=False, eps=1e-5):
+        """NeRF-style inverse-CDF sampling (models/Renderer.py:362-399)."""
+        w = weights + 1e-5
+        pdf = w / w.sum(-1, keepdim=True)
+        cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+        if det:
+            u = torch.linspace(0.0, 1.0, N_importance, device=bins.device, dtype=bins.dtype).expand(*cdf.shape[:-1], N_importance)
+        else:
+            u = torch.rand(*cdf.shape[:-1], N_importance, device=bins.device, dtype=bins.dtype)
+        u = u.contiguous()
+        inds = torch.searchsorted(cdf.detach(), u, right=False)
+        below, above = (inds - 1).clamp_min(0), inds.clamp_max(cdf.shape[-1] - 1)
+        c0, c1 = cdf.gather(-1, below), cdf.gather(-1, above)
+        b0, b1 = bins.gather(-1, below), bins.gather(-1, above)
+        denom = c1 - c0
+        denom = torch.where(denom < eps, torch.ones_like(denom), denom)
+        return b0 + (u - c0) / denom * (b1 - b0)

@@ -138,8 +138,8 @@ class KernelLog:
     def total(self):
         return sum(self.counts.values())
 
-    def begin(self, name):
-        self.counts[name] = self.counts.get(name, 0) + 1
+    def begin(self, name, n=1):
+        self.counts[name] = self.counts.get(name, 0) + n
         if self.timing:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
@@ -163,8 +163,8 @@ class KernelLog:
 KLOG = KernelLog()
 
 
-def _call(lib, name, fn, *args):
-    ev = KLOG.begin(name)
+def _call(lib, name, fn, *args, launches=1):
+    ev = KLOG.begin(name, launches)
     lib.check(fn(*args))
     KLOG.end(name, ev)
 
@@ -419,7 +419,8 @@ def sample_error_bounded_raw(lib, spec: FieldSpec, table, theta, beta_param, cen
     iters = torch.empty(r, device=dev)
     f = spec.c_field(lib, table, theta, image)
     _call(lib, "sample_error_bounded", lib.dll.ls2fm_sample_error_bounded, f, lib.ptr(beta_param), cfg, lib.ptr(center), lib.ptr(ray),
-          r, lib.ptr(ws), lib.ptr(t), lib.ptr(beta_plus), lib.ptr(iters), lib.stream())
+          r, lib.ptr(ws), lib.ptr(t), lib.ptr(beta_plus), lib.ptr(iters), lib.stream(),
+          launches=2 + 2 * (int(max_upsample_iter) + 1))     # init + (field forward + round) per round + finalize
     return t, beta_plus, iters
 
 

@@ -240,6 +240,7 @@ static inline float __fsub_rn(float a, float b) { volatile float r = a - b; retu
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
+static inline float __fdividef(float a, float b) { return a / b; }
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;

@@ -124,3 +124,24 @@ def test_port_matches_reference_golden_sampler():
     out = port.render_forward(gold["center"], gold["ray"], sdf_sd, rad_sd, cfg)
     gc.assert_close(out["rgb"], gold["out.rgb"], what="c2 rgb")
     gc.assert_close(out["depth_mlp"], gold["out.depth_mlp"], what="c2 depth")
+
+
+def test_renderer_api_compat_pieces_match_the_oracle():
+    """Renderer.composite / error_bound / sample_pdf stay callable with the reference's semantics (pure tensor math)."""
+    from levels2fm_b200.models.Renderer import Renderer
+    from . import common
+    ren = Renderer(common.make_opt("DTU", "cpu"))
+    g = torch.Generator().manual_seed(0)
+    d = torch.sort(torch.rand(2, 5, 20, generator=g) * 3, dim=-1).values
+    sdf = torch.randn(2, 5, 20, generator=g) * 0.3
+    a, b = torch.tensor(20.0), torch.tensor(0.05)
+    assert torch.allclose(ren.error_bound(d, sdf, a, b), port.error_bound(d, sdf, a, b), equal_nan=True)
+    w = torch.rand(2, 5, 19, generator=g)
+    assert torch.allclose(ren.sample_pdf(d, w, 12, det=True), port.sample_pdf_det(d, w, 12))
+    ray = torch.randn(2, 5, 3, generator=g)
+    rgbs = torch.rand(2, 5, 20, 3, generator=g)
+    sig = torch.rand(2, 5, 20, generator=g) * 5
+    r1, p1 = ren.composite(ray, rgbs, sig, d[..., None])
+    r2, p2 = port.composite(ray, rgbs, sig, d)
+    assert torch.allclose(r1, r2) and torch.allclose(p1, p2)
+    assert torch.allclose(ren.sdf_to_sigma(sdf, a, b), port.sdf_to_sigma(sdf, a, b))
