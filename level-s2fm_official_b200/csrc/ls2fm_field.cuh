@@ -26,6 +26,7 @@
 #pragma once
 
 #include "ls2fm_common.cuh"
+#include "ls2fm_tc.cuh"
 
 // ---------------------------------------------------------------- kernel-side parameter blocks
 struct LsNet {           // shared-memory placement of the staged MLP (floats)
@@ -38,6 +39,7 @@ struct LsNet {           // shared-memory placement of the staged MLP (floats)
     int rad_pitch;
     int warp_base;       // first float of the per-warp buffers
     int warp_stride;     // floats per warp
+    int tc_misc;         // backward kernel: mbarrier + TMEM slot (8 floats)
     int total;           // floats of dynamic shared memory
 };
 
@@ -79,7 +81,8 @@ inline LsNet ls_plan_net(const ls2fm_field_t& f, int rad_in_dim, int n_warps, bo
     const int hid = f.n_layers - 1;
     if (!backward) n.warp_stride = LS_WS * (LS_EROWS + LS_H * hid + LS_OROWS);
     else n.warp_stride = LS_WS * (2 * LS_EROWS + 2 * LS_H * hid + 2 * LS_H);
-    n.total = off + n.warp_stride * n_warps;
+    n.tc_misc = off + n.warp_stride * n_warps;
+    n.total = n.tc_misc + 8;
     return n;
 }
 
@@ -507,6 +510,14 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
     LS_DYN_SMEM(smem);
     ls_stage_weights(a, smem);
     __syncthreads();
+    // weight gradients of every layer but the last are accumulated by the tensor cores (tcgen05, 3xTF32) in TMEM for the
+    // whole lifetime of the persistent CTA: D_l[j][i] += sum_s zbar_l[s][j] * a_{l-1}[s][i] (+ tangent channel).  The panel
+    // layout of the activation buffers IS the K-major no-swizzle operand layout with K = sample (8-row x 16-byte core
+    // matrices, LBO = rows*16 B between the two 4-sample panels of a warp, one K = 8 step per warp tile).
+    LsTcBar* tc_bar = reinterpret_cast<LsTcBar*>(smem + a.net.tc_misc);
+    const uint32_t tmem = ls_tc_alloc(reinterpret_cast<uint32_t*>(smem + a.net.tc_misc + 4));
+    ls_tc_bar_init(tc_bar);
+    uint32_t tc_phase = 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = a.f.n_levels;
@@ -529,21 +540,20 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
     const int RP = a.net.rad_pitch;
     const float* Weff = smem + a.net.weff_off;
 
-    // persistent register accumulators
-    float wacc[LS2FM_MAX_LAYERS][4][4];
+    // persistent register accumulators: bias gradients of every layer, weight gradient of the (small) output layer
+    float wlast[4][4];
     float bacc[LS2FM_MAX_LAYERS];
 #pragma unroll
-    for (int l = 0; l < LS2FM_MAX_LAYERS; ++l) {
-        bacc[l] = 0.f;
+    for (int l = 0; l < LS2FM_MAX_LAYERS; ++l) bacc[l] = 0.f;
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) wacc[l][p][q] = 0.f;
-    }
+        for (int q = 0; q < 4; ++q) wlast[p][q] = 0.f;
     float weff_acc = 0.f;
 
     const int64_t n_ctiles = (a.p.n + LS_WS * LS_BW_WARPS - 1) / (LS_WS * LS_BW_WARPS);
     for (int64_t ct = blockIdx.x; ct < n_ctiles; ct += gridDim.x) {
+        const bool first_step = ct == (int64_t)blockIdx.x;
         // ------------------------------------------------ B1: upstream gradients of this sample
         const int64_t i_in = (ct * LS_BW_WARPS + warp) * LS_WS + s8;
         const bool valid = i_in < a.p.n;
@@ -745,49 +755,39 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
             const int o_z = last ? oP : oA + l * 2 * LS_WS * LS_H;
             const int o_zd = last ? oPd : o_z + LS_WS * LS_H;
             const int n_zrows = last ? LS_OROWS : LS_H;
-            // ---- (a) weight-gradient GEMM over the 64 samples of the CTA step
-            {
-                int rin[4], rz[4];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) { int r = bi + 16 * p; rin[p] = r < R_in ? r : R_in - 1; }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { int r = bj + 16 * q; rz[q] = r < n_zrows ? r : n_zrows - 1; }
-                float bsum = 0.f;
-                const int brow = tid < n_zrows ? tid : n_zrows - 1;
-#pragma unroll 1
-                for (int w = 0; w < LS_BW_WARPS; ++w) {
-                    const float* base = WB + w * WSTR;
-#pragma unroll 1
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        // compile-time pruning: layer 0 has <= 36 input rows (p < 3), the output layer <= 20 columns (q < 2)
-                        const int PM = (l == 0) ? 3 : 4, QM = (l == K - 1) ? 2 : 4;   // constants once the layer loop is unrolled
-                        float4 iv[4], zv[4];
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) if (p < PM) iv[p] = ls_ld4(ls_row(base + o_in, R_in, h2, rin[p]));
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) if (q < QM) zv[q] = ls_ld4(ls_row(base + o_z, LS_H, h2, rz[q]));
-#pragma unroll
-                        for (int p = 0; p < 4; ++p)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (p < PM && q < QM) wacc[l][p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wacc[l][p][q]))));
-                        if (TAN) {
-#pragma unroll
-                            for (int p = 0; p < 4; ++p) if (p < PM) iv[p] = ls_ld4(ls_row(base + o_ind, R_in, h2, rin[p]));
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) if (q < QM) zv[q] = ls_ld4(ls_row(base + o_zd, LS_H, h2, rz[q]));
-#pragma unroll
-                            for (int p = 0; p < 4; ++p)
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    if (p < PM && q < QM) wacc[l][p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wacc[l][p][q]))));
-                        }
-                        const float4 bz = ls_ld4(ls_row(base + o_z, LS_H, h2, brow));
-                        bsum += bz.x + bz.y + bz.z + bz.w;
-                    }
-                }
-                bacc[l] += bsum;
+            // ---- weight gradient of hidden / input layers on the tensor cores (tcgen05, 3xTF32), one batch per channel.
+            //      The raw fp32 tiles are read as tf32 by truncation ("hi"); each warp writes what the truncation drops of its
+            //      own 8 samples ("lo") into P (zbar) and Pd (layer input); thread 0 issues lo*hi + hi*lo + hi*hi for the 8 warp
+            //      tiles (K = 64 samples).  The batches run under the SIMT work that follows them.
+#define LS_BW_TC_BATCH(CH)                                                                                           \
+            if (!last) {                                                                                             \
+                const int d_col = 64 * l, n_cols = l == 0 ? 48 : 64;                                                 \
+                const int oz = (CH) ? o_zd : o_z, oi = (CH) ? o_ind : o_in;                                          \
+                for (int e = lane; e < 2 * LS_H; e += 32) {                                                          \
+                    float4 v = ls_ld4(my + oz + 4 * e);                                                              \
+                    v.x = ls_tf32_lo(v.x); v.y = ls_tf32_lo(v.y); v.z = ls_tf32_lo(v.z); v.w = ls_tf32_lo(v.w);      \
+                    ls_st4(P + 4 * e, v);                                                                            \
+                }                                                                                                    \
+                for (int e = lane; e < 2 * R_in; e += 32) {                                                          \
+                    const int h2 = e / R_in, row = e - h2 * R_in;                                                    \
+                    float4 v = ls_ld4(ls_row(my + oi, R_in, h2, row));                                               \
+                    v.x = ls_tf32_lo(v.x); v.y = ls_tf32_lo(v.y); v.z = ls_tf32_lo(v.z); v.w = ls_tf32_lo(v.w);      \
+                    ls_st4(ls_row(Pd, LS_H, h2, row), v);                                                            \
+                }                                                                                                    \
+                ls_fence_smem_to_async();                                                                            \
+                ls_tc_sync_before_mma();                                                                             \
+                if (tid == 0) {                                                                                      \
+                    for (int w = 0; w < LS_BW_WARPS; ++w) {                                                          \
+                        const float* base = WB + w * WSTR;                                                           \
+                        const bool acc0 = !(first_step && (CH) == 0 && w == 0);                                      \
+                        ls_tc_mma_ss(tmem, d_col, base + oP, LS_H * 16, base + oi, R_in * 16, n_cols, acc0);         \
+                        ls_tc_mma_ss(tmem, d_col, base + oz, LS_H * 16, base + oPd, LS_H * 16, n_cols, true);        \
+                        ls_tc_mma_ss(tmem, d_col, base + oz, LS_H * 16, base + oi, R_in * 16, n_cols, true);         \
+                    }                                                                                                \
+                    ls_tc_commit(tc_bar);                                                                            \
+                }                                                                                                    \
             }
+            LS_BW_TC_BATCH(0)
             // ---- (b) input adjoints  abar = W^T zbar, abar_dot = W^T zbar_dot  (own warp tile)
             float acc[4][4], accd[4][4];
 #pragma unroll
@@ -798,6 +798,65 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                                                    my + o_z, my + o_zd, LS_H, sg, og, acc, accd);
             else ls_prod_rev<TAN ? 2 : 1, 3>(smem + a.net.sw_off[l], a.net.pitch[l], n_in, last ? LS_OROWS : LS_H,
                                              my + o_z, my + o_zd, LS_H, sg, og, acc, accd);
+            if (TAN && !last) {
+                ls_tc_wait(tc_bar, tc_phase);          // primal batch done: P / Pd are free again
+                LS_BW_TC_BATCH(1)
+            }
+#undef LS_BW_TC_BATCH
+            // ---- (a) bias gradient (all layers) and, for the output layer, the weight gradient on the SIMT pipes
+            {
+                float bsum = 0.f;
+                const int brow = tid < n_zrows ? tid : n_zrows - 1;
+                if (last) {
+                    int rin[4], rz[2];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) rin[p] = bi + 16 * p;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) { int r = bj + 16 * q; rz[q] = r < n_zrows ? r : n_zrows - 1; }
+#pragma unroll 1
+                    for (int w = 0; w < LS_BW_WARPS; ++w) {
+                        const float* base = WB + w * WSTR;
+#pragma unroll 1
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            float4 iv[4], zv[2];
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) iv[p] = ls_ld4(ls_row(base + o_in, R_in, h2, rin[p]));
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) zv[q] = ls_ld4(ls_row(base + o_z, LS_H, h2, rz[q]));
+#pragma unroll
+                            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                                for (int q = 0; q < 2; ++q)
+                                    wlast[p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wlast[p][q]))));
+                            if (TAN) {
+#pragma unroll
+                                for (int p = 0; p < 4; ++p) iv[p] = ls_ld4(ls_row(base + o_ind, R_in, h2, rin[p]));
+#pragma unroll
+                                for (int q = 0; q < 2; ++q) zv[q] = ls_ld4(ls_row(base + o_zd, LS_H, h2, rz[q]));
+#pragma unroll
+                                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                                    for (int q = 0; q < 2; ++q)
+                                        wlast[p][q] = fmaf(iv[p].w, zv[q].w, fmaf(iv[p].z, zv[q].z, fmaf(iv[p].y, zv[q].y, fmaf(iv[p].x, zv[q].x, wlast[p][q]))));
+                            }
+                            const float4 bz = ls_ld4(ls_row(base + o_z, LS_H, h2, brow));
+                            bsum += bz.x + bz.y + bz.z + bz.w;
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int w = 0; w < LS_BW_WARPS; ++w) {
+                        const float* base = WB + w * WSTR;
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const float4 bz = ls_ld4(ls_row(base + o_z, LS_H, h2, brow));
+                            bsum += bz.x + bz.y + bz.z + bz.w;
+                        }
+                    }
+                }
+                bacc[l] += bsum;
+            }
+            if (!last) ls_tc_wait(tc_bar, tc_phase);     // the tensor cores are done with the tiles of layer l (and with P / Pd)
             __syncthreads();     // everybody is done reading the activations of layer l
             // ---- (c) through the activation (in place) or out to the encoding adjoints
             if (l > 0) {
@@ -874,17 +933,39 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
 
     // ------------------------------------------------ flush the parameter gradients
     if (a.d_theta) {
+        // tensor-core accumulators: TMEM lane j (warps 0, 1 own lanes 0..63) holds row j = output unit, column i = input unit
+        if (warp < 2 && n_ctiles > (int64_t)blockIdx.x) {
+#pragma unroll 1
+            for (int l = 0; l < K - 1; ++l) {
+                const int n_in = a.f.dims[l], n_out = a.f.dims[l + 1];
+                const int jrow = tid;                      // 0..63
+#pragma unroll 1
+                for (int c = 0; c < 64; c += 16) {
+                    if (c < n_in) {
+                        float v[16];
+                        ls_tmem_ld(tmem, 64 * l + c, v, 16);
 #pragma unroll
-        for (int l = 0; l < LS2FM_MAX_LAYERS; ++l) {
-            if (l >= K) continue;
+                        for (int q = 0; q < 16; ++q)
+                            if (c + q < n_in && jrow < n_out) atomicAdd(a.d_theta + a.net.gw_off[l] + (c + q) * n_out + jrow, v[q]);
+                    }
+                }
+            }
+        }
+        {
+            const int l = K - 1;
             const int n_in = a.f.dims[l], n_out = a.f.dims[l + 1];
 #pragma unroll
             for (int p = 0; p < 4; ++p)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 2; ++q) {
                     const int ii = bi + 16 * p, jj = bj + 16 * q;
-                    if (ii < n_in && jj < n_out) atomicAdd(a.d_theta + a.net.gw_off[l] + ii * n_out + jj, wacc[l][p][q]);
+                    if (ii < n_in && jj < n_out) atomicAdd(a.d_theta + a.net.gw_off[l] + ii * n_out + jj, wlast[p][q]);
                 }
+        }
+#pragma unroll
+        for (int l = 0; l < LS2FM_MAX_LAYERS; ++l) {
+            if (l >= K) continue;
+            const int n_out = a.f.dims[l + 1];
             if (tid < n_out) atomicAdd(a.d_theta + a.net.gb_off[l] + tid, bacc[l]);
         }
     }
@@ -893,4 +974,5 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
         if (tid < 3 * in_dim) atomicAdd(a.d_w_eff + tid, weff_acc);
         else if (tid < 3 * in_dim + 3 && a.d_b_eff) atomicAdd(a.d_b_eff + (tid - 3 * in_dim), weff_acc);
     }
+    ls_tc_dealloc(tmem);
 }

@@ -55,8 +55,23 @@ LS_DEV void ls_tc_mma(uint32_t, int d_col, int a_col, const float* B, int N, int
             t.v[m][d_col + n] = acc;
         }
 }
+// one K = 8 step with BOTH operands in shared memory (K-major, SBO = 128 B, per-operand LBO): D[m][d_col+n] (+)= sum_k A(m,k) B(n,k)
+LS_DEV void ls_tc_mma_ss(uint32_t, int d_col, const float* A, int a_lbo, const float* B, int b_lbo, int N, bool accumulate) {
+    LsTmemSim& t = ls_tmem_sim();
+    for (int m = 0; m < LS_TC_M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float acc = accumulate ? t.v[m][d_col + n] : 0.f;
+            for (int k = 0; k < 8; ++k) {
+                const float av = *(const float*)((const char*)A + (k >> 2) * a_lbo + (m >> 3) * 128 + (m & 7) * 16 + (k & 3) * 4);
+                const float bv = *(const float*)((const char*)B + (k >> 2) * b_lbo + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4);
+                acc += ls_tf32_trunc(av) * ls_tf32_trunc(bv);
+            }
+            t.v[m][d_col + n] = acc;
+        }
+}
 LS_DEV void ls_tc_commit(LsTcBar* b) { b->arrived += 1; }
 LS_DEV void ls_tc_wait(LsTcBar*, uint32_t& phase) { __syncthreads(); phase ^= 1; }
+LS_DEV float ls_tf32_lo(float x) { return x - ls_tf32_trunc(x); }
 LS_DEV void ls_split_tf32(float v, float& hi, float& lo) { hi = ls_tf32_round(v); lo = v - hi; }
 LS_DEV void ls_fence_smem_to_async() {}
 #else
@@ -142,6 +157,17 @@ LS_DEV void ls_tc_mma(uint32_t tmem, int d_col, int a_col, const float* B, int N
                      :: "r"(tmem + (uint32_t)d_col), "r"(tmem + (uint32_t)(a_col + kb * 8)), "l"(bdesc), "r"(idesc), "r"(acc));
     }
 }
+// one K = 8 step with BOTH operands in shared memory (K-major, SBO = 128 B, per-operand LBO)
+LS_DEV void ls_tc_mma_ss(uint32_t tmem, int d_col, const float* A, int a_lbo, const float* B, int b_lbo, int N, bool accumulate) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(LS_TC_M >> 4) << 24);
+    const uint64_t adesc = ls_tc_desc(ls_smem_u32(A), (uint32_t)a_lbo, 128);
+    const uint64_t bdesc = ls_tc_desc(ls_smem_u32(B), (uint32_t)b_lbo, 128);
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem + (uint32_t)d_col), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc));
+}
+// what the tensor core drops when it reads an fp32 word as tf32 (truncation): x - trunc_tf32(x), exact in fp32
+LS_DEV float ls_tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 LS_DEV void ls_tc_commit(LsTcBar* b) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(ls_smem_u32(b)) : "memory");
 }

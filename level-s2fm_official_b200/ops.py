@@ -210,14 +210,14 @@ def field_prepare_raw(lib, spec: FieldSpec, table, theta, rad: Optional[_C.Radia
 
 
 def field_forward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: Optional[_C.Radiance],
-                      want_y=False, want_sdf=True, want_nrm=False, want_rgb=False, image=None):
+                      want_y=False, want_sdf=True, want_nrm=False, want_rgb=False, image=None, simt=False):
     n, dev = int(pts.n), table.device
     y = torch.empty(n, spec.dout, device=dev) if want_y else None
     sdf = torch.empty(n, device=dev) if want_sdf else None
     nrm = torch.empty(n, 3, device=dev) if want_nrm else None
     rgb = torch.empty(n, 3, device=dev) if want_rgb else None
     f = spec.c_field(lib, table, theta, image)
-    _call(lib, "field_forward", lib.dll.ls2fm_field_forward, f, pts, rad, lib.ptr(y), lib.ptr(sdf), lib.ptr(nrm), lib.ptr(rgb), lib.stream())
+    _call(lib, "field_forward_simt" if simt else "field_forward", lib.dll.ls2fm_field_forward_simt if simt else lib.dll.ls2fm_field_forward, f, pts, rad, lib.ptr(y), lib.ptr(sdf), lib.ptr(nrm), lib.ptr(rgb), lib.stream())
     return y, sdf, nrm, rgb
 
 

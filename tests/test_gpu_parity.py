@@ -158,3 +158,32 @@ def test_errors_are_raised(product_lib):
 
 def test_fused_sphere_trace_kernel_internals():
     gc.sphere_trace_internals(DEV)
+
+
+@pytest.mark.parametrize("n_levels,layers", [(16, (None, 64, 64, 64, 16)), (16, (None, 64, 16)), (4, (None, 64, 64, 16)), (8, (None, 64, 16))])
+def test_tensor_core_forward_matches_simt_forward_and_operand_image(product_lib, n_levels, layers):
+    """The tcgen05 (3xTF32) forward kernel, the fp32-SIMT forward kernel and the prepared-operand-image path are three
+    routes to the same numbers: 1e-5 relative on sdf / features / normals / colours, on ragged sizes."""
+    from levels2fm_b200 import ops
+    opt = common.make_opt("DTU", DEV, n_levels, layers, 32)
+    cfg = common.cfg_of(opt, n_levels)
+    sdf_sd, rad_sd = port.random_state(cfg, seed=9, table_std=0.2)
+    sdf, rad, ren = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    rad.load_state_dict(rad_sd)
+    center, ray = common.make_rays(1, 37, 1.0, seed=5)
+    c2, r2 = center.reshape(-1, 3).contiguous().to(DEV), ray.reshape(-1, 3).contiguous().to(DEV)
+    t, _ = ops.sample_uniform_raw(product_lib, c2, r2, 29, cfg.bound_min, cfg.bound_max)       # 37 x 29 = 1073 samples (ragged)
+    theta = sdf.SDF_MLP.theta().detach().contiguous()
+    w_eff, b_eff = rad.Rad_dec.effective_affine()
+    rs = ops._rad(product_lib, rad.rad_spec(), w_eff.detach(), b_eff.detach(), None)
+    pts = ops._points(product_lib, None, c2, r2, t)
+    spec, table = sdf.field_spec(), sdf.table().detach()
+    kw = dict(want_y=True, want_nrm=True, want_rgb=True)
+    tc = ops.field_forward_raw(product_lib, spec, table, theta, pts, rs, **kw)
+    simt = ops.field_forward_raw(product_lib, spec, table, theta, pts, rs, simt=True, **kw)
+    image = ops.field_prepare_raw(product_lib, spec, table, theta, rs)
+    img = ops.field_forward_raw(product_lib, spec, table, theta, pts, rs, image=image, **kw)
+    for a, b, c, name in zip(tc, simt, img, ("y", "sdf", "nrm", "rgb")):
+        assert common.rel_err(a.cpu(), b.cpu()) < 1e-5, name
+        assert torch.equal(a, c), name + " (operand image)"
