@@ -212,7 +212,7 @@ def main():
     def step(c, r, g):
         bucket.zero()
         out = ren.forward(opt, c, r, sdf, rad)
-        loss = synthetic.render_loss(out, g)
+        loss = synthetic.render_loss_fused(out, g)
         loss.backward()
         bucket.allreduce()
         return loss, out

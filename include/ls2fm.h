@@ -223,6 +223,14 @@ int ls2fm_sphere_trace(const ls2fm_field_t* sdf_field, const float* ray0, const 
                        float sdf_threshold, int32_t iters_max, float* track, int32_t* n_unfinished,
                        float* t_near, float* t_far, float* acc_end, void* stream);
 
+/* ------------------------------------------------------------------ rendering-loss tail
+ * The rendering losses every stage computes on the renderer's outputs (pipelines/rendering_refine.py:99-121,
+ * BA.py:190-204, Initialization.py:251-261): sums[0] = sum |rgb - gt| over [R,3], sums[1] = sum | ||n|| - 1 | over the
+ * per-sample normals [S,3], and -- in the same pass -- the gradients of w_rgb * mean_L1 + w_eik * mean_eikonal
+ * w.r.t. rgb (g_rgb [R,3]) and the normals (g_normals [S,3]); both nullable. */
+int ls2fm_render_loss(const float* rgb, const float* gt, int64_t n_rays, const float* normals, int64_t n_samples,
+                      float w_rgb, float w_eik, float* sums, float* g_rgb, float* g_normals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

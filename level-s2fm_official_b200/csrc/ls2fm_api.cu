@@ -429,4 +429,19 @@ int ls2fm_sphere_trace(const ls2fm_field_t* sdf_field, const float* ray0, const 
     return ls_check_launch("sphere_trace");
 }
 
+int ls2fm_render_loss(const float* rgb, const float* gt, int64_t n_rays, const float* normals, int64_t n_samples, float w_rgb,
+                      float w_eik, float* sums, float* g_rgb, float* g_normals, void* stream) {
+    if (n_rays < 0 || n_samples < 0 || !sums) return ls_fail("render_loss: bad arguments");
+    if ((n_rays > 0 && (!rgb || !gt)) || (n_samples > 0 && !normals)) return ls_fail("render_loss: NULL input");
+    ls_memset_async(sums, 0, 2 * sizeof(float), stream);
+    if (n_rays == 0 && n_samples == 0) return 0;
+    const int bs = 256;
+    int64_t work = n_samples > 3 * n_rays ? n_samples : 3 * n_rays;
+    int64_t grid = (work + bs - 1) / bs;
+    if (grid > 4 * ls_sm_count()) grid = 4 * ls_sm_count();
+    LS_LAUNCH(ls_render_loss_kernel, (unsigned)grid, bs, 0, stream, rgb, gt, 3 * n_rays, normals, n_samples, w_rgb, w_eik, sums, g_rgb,
+              g_normals);
+    return ls_check_launch("render_loss");
+}
+
 }  // extern "C"

@@ -139,7 +139,7 @@ LS_DEV void ls_prod_rev(const float* Wt, int pitch, int n_rows, int n_j, const f
     }
     const float* p0 = z0 + sg * R * 4;
     const float* p1 = z1 + sg * R * 4;
-#pragma unroll 1
+#pragma unroll 2
     for (int j = 0; j < n_j; j += 4) {
         float4 w[NQ];
 #pragma unroll

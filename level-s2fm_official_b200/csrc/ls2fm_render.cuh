@@ -285,3 +285,37 @@ __global__ void ls_grid_encode_backward_kernel(const ls2fm_field_t f, const floa
         atomicAdd(d_u + 3 * i + 2, scale * du[2]);
     }
 }
+
+// ---------------------------------------------------------------- rendering-loss tail
+// loss = w_rgb * mean|rgb - gt| + w_eik * mean| ||n|| - 1 |   (pipelines/rendering_refine.py:99-121, BA.py:190-204)
+// One pass over rgb [R,3] / gt [R,3] and the per-sample normals [S,3]: partial sums by warp shuffle + one atomic per
+// warp into sums[0] (rgb L1 sum), sums[1] (eikonal sum); the same pass writes the gradients of the two MEANS
+// (unit upstream gradient; the autograd wrapper scales them): g_rgb = sign(rgb - gt) / (3R), g_nrm = sign(||n|| - 1) n / ||n|| / S.
+__global__ void ls_render_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, int64_t n_rgb,
+                                      const float* __restrict__ nrm, int64_t n_samples, float w_rgb, float w_eik,
+                                      float* __restrict__ sums, float* __restrict__ g_rgb, float* __restrict__ g_nrm) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    float s_rgb = 0.f, s_eik = 0.f;
+    for (int64_t i = gid; i < n_rgb; i += stride) {
+        const float d = rgb[i] - gt[i];
+        s_rgb += fabsf(d);
+        if (g_rgb) g_rgb[i] = (d > 0.f ? w_rgb : (d < 0.f ? -w_rgb : 0.f)) / (float)n_rgb;
+    }
+    for (int64_t i = gid; i < n_samples; i += stride) {
+        const float x = nrm[3 * i], y = nrm[3 * i + 1], z = nrm[3 * i + 2];
+        const float len = sqrtf(x * x + y * y + z * z);
+        const float e = len - 1.f;
+        s_eik += fabsf(e);
+        if (g_nrm) {
+            const float k = len > 0.f ? (e > 0.f ? w_eik : (e < 0.f ? -w_eik : 0.f)) / (len * (float)n_samples) : 0.f;
+            g_nrm[3 * i] = k * x; g_nrm[3 * i + 1] = k * y; g_nrm[3 * i + 2] = k * z;
+        }
+    }
+    s_rgb = ls_warp_sum(s_rgb);
+    s_eik = ls_warp_sum(s_eik);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sums, s_rgb);
+        atomicAdd(sums + 1, s_eik);
+    }
+}

@@ -437,3 +437,31 @@ def sphere_trace_raw(lib, spec: FieldSpec, table, theta, ray0, ray_dir, sdf_thre
     _call(lib, "sphere_trace", lib.dll.ls2fm_sphere_trace, f, lib.ptr(ray0), lib.ptr(ray_dir), m, float(sdf_threshold), int(iters_max),
           lib.ptr(track), lib.ptr(cnt, torch.int32), lib.ptr(t_near), lib.ptr(t_far), lib.ptr(acc_end), lib.stream())
     return track, cnt, t_near, t_far, acc_end
+
+
+class RenderLoss(torch.autograd.Function):
+    """w_rgb * mean|rgb - gt| + w_eik * mean| ||normals|| - 1 | in one kernel (forward value and both gradients in the
+    same pass); the rendering-loss tail of pipelines/rendering_refine.py:99-121 / BA.py:190-204.
+    forward(rgb [...,3], gt [...,3], normals [...,3], w_rgb, w_eik) -> (loss, rgb_l1_mean, eikonal_mean)"""
+
+    @staticmethod
+    def forward(ctx, rgb, gt, normals, w_rgb, w_eik):
+        lib = _C.get()
+        rgb_c, gt_c, nrm_c = rgb.detach().contiguous(), gt.detach().contiguous(), normals.detach().contiguous()
+        n_rays, n_samples = rgb_c.numel() // 3, nrm_c.numel() // 3
+        sums = torch.empty(2, device=rgb.device)
+        g_rgb = torch.empty_like(rgb_c)
+        g_nrm = torch.empty_like(nrm_c)
+        _call(lib, "render_loss", lib.dll.ls2fm_render_loss, lib.ptr(rgb_c), lib.ptr(gt_c), n_rays, lib.ptr(nrm_c), n_samples,
+              float(w_rgb), float(w_eik), lib.ptr(sums), lib.ptr(g_rgb), lib.ptr(g_nrm), lib.stream())
+        ctx.save_for_backward(g_rgb, g_nrm)
+        l1 = sums[0] / max(3 * n_rays, 1)
+        eik = sums[1] / max(n_samples, 1)
+        out = w_rgb * l1 + w_eik * eik
+        ctx.mark_non_differentiable(l1, eik)
+        return out, l1, eik
+
+    @staticmethod
+    def backward(ctx, g_out, _g1, _g2):
+        g_rgb, g_nrm = ctx.saved_tensors
+        return g_rgb * g_out, None, g_nrm * g_out, None, None

@@ -67,6 +67,12 @@ def init_fields(sdf, rad, regime: str = "init", seed: int = 0):
         l0.weight_g.copy_(w.norm(dim=1, keepdim=True))
 
 
+def render_loss_fused(out, gt):
+    """Same value and gradients as render_loss, through the fused loss kernel (ops.RenderLoss)."""
+    from . import ops
+    return ops.RenderLoss.apply(out["rgb"], gt, out["normals"], 1e3, 1e2)[0]
+
+
 def render_loss(out, gt):
     """The rendering losses of the reference's refine stage (pipelines/rendering_refine.py:99-121 with the
     log10 weights rgb: 3, eikonal_loss: 2 of options/LevelS2fM.yaml:120-122)."""

@@ -187,3 +187,18 @@ def test_tensor_core_forward_matches_simt_forward_and_operand_image(product_lib,
     for a, b, c, name in zip(tc, simt, img, ("y", "sdf", "nrm", "rgb")):
         assert common.rel_err(a.cpu(), b.cpu()) < 1e-5, name
         assert torch.equal(a, c), name + " (operand image)"
+
+
+def test_fused_render_loss_matches_torch():
+    from levels2fm_b200 import synthetic
+    g = torch.Generator().manual_seed(0)
+    rgb = torch.rand(2, 700, 3, generator=g).to(DEV).requires_grad_(True)
+    gt = torch.rand(2, 700, 3, generator=g).to(DEV)
+    nrm = (torch.randn(2, 700, 33, 3, generator=g) * 1.3).to(DEV).requires_grad_(True)
+    ref = synthetic.render_loss({"rgb": rgb, "normals": nrm}, gt)
+    gr_ref = torch.autograd.grad(ref, [rgb, nrm])
+    out = synthetic.render_loss_fused({"rgb": rgb, "normals": nrm}, gt)
+    gr = torch.autograd.grad(out, [rgb, nrm])
+    assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
+    for a, b in zip(gr, gr_ref):
+        assert common.rel_err(a.cpu(), b.cpu()) < 1e-5

@@ -98,3 +98,18 @@ def test_error_bounded_sampler_hard_cases(eps, N, std):
 
 def test_fused_sphere_trace_kernel_internals():
     gc.sphere_trace_internals("cpu")
+
+
+def test_fused_render_loss_matches_torch():
+    from levels2fm_b200 import ops, synthetic
+    g = torch.Generator().manual_seed(0)
+    rgb = torch.rand(2, 7, 3, generator=g, requires_grad=True)
+    gt = torch.rand(2, 7, 3, generator=g)
+    nrm = (torch.randn(2, 7, 5, 3, generator=g) * 1.3).requires_grad_(True)
+    ref = synthetic.render_loss({"rgb": rgb, "normals": nrm}, gt)
+    gr_ref = torch.autograd.grad(ref, [rgb, nrm])
+    out = synthetic.render_loss_fused({"rgb": rgb, "normals": nrm}, gt)
+    gr = torch.autograd.grad(out * 1.0, [rgb, nrm])
+    assert abs(out.item() - ref.item()) < 1e-4 * abs(ref.item())
+    for a, b in zip(gr, gr_ref):
+        assert common.rel_err(a, b) < 1e-5
