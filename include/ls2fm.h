@@ -130,6 +130,25 @@ int ls2fm_grid_encode(const ls2fm_field_t* field, const float* u, int64_t m,
 int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64_t m,
                                const float* g_enc, float* d_table, float* d_u, void* stream);
 
+/* ------------------------------------------------------------------ parameter preparation
+ * One weight-normed linear layer as the reference stores it (nn.utils.weight_norm, models/base.py:200,241):
+ * W = g * v / ||v||_row.  dg / dv / db are the backward outputs (written, same shapes); ignored by the forward. */
+typedef struct {
+    const float* g;       /* device [dout]      weight_g */
+    const float* v;       /* device [dout, din] weight_v */
+    const float* b;       /* device [dout]      bias */
+    float* dg; float* dv; float* db;
+    int32_t din, dout;
+} ls2fm_param_layer_t;
+/* forward: geometry MLP layers (n_geo <= 4, nullable) -> theta (packed W_l^T, b_l); radiance decoder (exactly 3 layers
+ * in -> 64 -> 64 -> 3, nullable) -> w_eff [3, in] = W3 W2 W1 and b_eff [3] (the reference applies no hidden activation,
+ * models/base.py:230,257).  One launch instead of ~30 eager kernels. */
+int ls2fm_params_forward(const ls2fm_param_layer_t* geo, int32_t n_geo, const ls2fm_param_layer_t* rad,
+                         float* theta, float* w_eff, float* b_eff, void* stream);
+/* backward: d_theta / d_w_eff / d_b_eff (nullable) -> dg, dv, db of every layer (written). */
+int ls2fm_params_backward(const ls2fm_param_layer_t* geo, int32_t n_geo, const ls2fm_param_layer_t* rad,
+                          const float* d_theta, const float* d_w_eff, const float* d_b_eff, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core operand image
  * The tcgen05 forward kernel wants the weights as hi/lo TF32 operands in its shared-memory layout (W_l and W_l^T, K-major
  * core matrices, biases, W_eff).  ls2fm_field_prepare converts theta (+ the radiance block, nullable) ONCE into `image`

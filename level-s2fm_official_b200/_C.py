@@ -49,6 +49,11 @@ class Points(C.Structure):
                 ("out_stride", C.c_int32), ("out_offset", C.c_int32)]
 
 
+class ParamLayer(C.Structure):
+    _fields_ = [("g", C.c_void_p), ("v", C.c_void_p), ("b", C.c_void_p), ("dg", C.c_void_p), ("dv", C.c_void_p), ("db", C.c_void_p),
+                ("din", C.c_int32), ("dout", C.c_int32)]
+
+
 class SamplerCfg(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_final", C.c_int32), ("max_upsample_iter", C.c_int32),
                 ("max_bisection_itr", C.c_int32), ("eps", C.c_float), ("beta_speed", C.c_float)]
@@ -72,6 +77,8 @@ SIGNATURES = {
     "ls2fm_ray_aabb": (C.c_int, [_VP, _VP, C.c_int64, _F3, _F3, _VP, _VP, _VP]),
     "ls2fm_grid_encode": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP]),
     "ls2fm_grid_encode_backward": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    "ls2fm_params_forward": (C.c_int, [C.POINTER(ParamLayer), C.c_int32, C.POINTER(ParamLayer), _VP, _VP, _VP, _VP]),
+    "ls2fm_params_backward": (C.c_int, [C.POINTER(ParamLayer), C.c_int32, C.POINTER(ParamLayer), _VP, _VP, _VP, _VP]),
     "ls2fm_field_image_floats": (C.c_int64, [C.POINTER(Field), C.POINTER(Radiance)]),
     "ls2fm_field_prepare": (C.c_int, [C.POINTER(Field), C.POINTER(Radiance), _VP, _VP]),
     "ls2fm_field_forward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),

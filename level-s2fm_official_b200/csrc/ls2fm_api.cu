@@ -10,6 +10,7 @@
 #include "ls2fm_render.cuh"
 #include "ls2fm_sampler.cuh"
 #include "ls2fm_trace.cuh"
+#include "ls2fm_params.cuh"
 
 static thread_local std::string g_err;
 
@@ -189,6 +190,52 @@ int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64
     const int64_t total = m * field->n_levels;
     LS_LAUNCH(ls_grid_encode_backward_kernel, (unsigned)((total + bs - 1) / bs), bs, 0, stream, *field, u, m, g_enc, d_table, d_u);
     return ls_check_launch("grid_encode_backward");
+}
+
+static int ls_fill_params(LsParamArgs& a, const ls2fm_param_layer_t* geo, int32_t n_geo, const ls2fm_param_layer_t* rad, bool backward) {
+    memset(&a, 0, sizeof(a));
+    if (n_geo < 0 || n_geo > LS2FM_MAX_LAYERS || (n_geo > 0 && !geo)) return ls_fail("params: bad geometry layer list");
+    for (int l = 0; l < n_geo; ++l) {
+        a.geo[l] = geo[l];
+        if (!geo[l].g || !geo[l].v || !geo[l].b || geo[l].din < 1 || geo[l].dout < 1) return ls_fail("params: NULL / empty geometry layer");
+        if (backward && (!geo[l].dg || !geo[l].dv || !geo[l].db)) return ls_fail("params: NULL geometry gradient output");
+    }
+    a.n_geo = n_geo;
+    if (rad) {
+        for (int l = 0; l < 3; ++l) {
+            a.rad[l] = rad[l];
+            if (!rad[l].g || !rad[l].v || !rad[l].b) return ls_fail("params: NULL radiance layer");
+            if (backward && (!rad[l].dg || !rad[l].dv || !rad[l].db)) return ls_fail("params: NULL radiance gradient output");
+        }
+        if (rad[0].dout != LS_H || rad[1].din != LS_H || rad[1].dout != LS_H || rad[2].din != LS_H || rad[2].dout != 3 ||
+            rad[0].din < 1 || rad[0].din > LS_PP_MAX_IN)
+            return ls_fail("params: the radiance decoder must be in -> 64 -> 64 -> 3 with in <= 68");
+        a.has_rad = 1;
+    }
+    return 0;
+}
+
+int ls2fm_params_forward(const ls2fm_param_layer_t* geo, int32_t n_geo, const ls2fm_param_layer_t* rad, float* theta, float* w_eff,
+                         float* b_eff, void* stream) {
+    LsParamArgs a;
+    if (ls_fill_params(a, geo, n_geo, rad, false)) return 1;
+    if ((n_geo > 0 && !theta) || (rad && (!w_eff || !b_eff))) return ls_fail("params_forward: NULL output");
+    a.theta = theta; a.w_eff = w_eff; a.b_eff = b_eff;
+    const int smem = LS_PP_SMEM_FLOATS * (int)sizeof(float);
+    if (ls_opt_in_smem(ls_params_forward_kernel, smem)) return 1;
+    LS_LAUNCH(ls_params_forward_kernel, (unsigned)(1 + n_geo), LS_PP_THREADS, smem, stream, a);
+    return ls_check_launch("params_forward");
+}
+
+int ls2fm_params_backward(const ls2fm_param_layer_t* geo, int32_t n_geo, const ls2fm_param_layer_t* rad, const float* d_theta,
+                          const float* d_w_eff, const float* d_b_eff, void* stream) {
+    LsParamArgs a;
+    if (ls_fill_params(a, geo, n_geo, rad, true)) return 1;
+    a.d_theta = d_theta; a.d_w_eff = d_w_eff; a.d_b_eff = d_b_eff;
+    const int smem = LS_PP_SMEM_FLOATS * (int)sizeof(float);
+    if (ls_opt_in_smem(ls_params_backward_kernel, smem)) return 1;
+    LS_LAUNCH(ls_params_backward_kernel, (unsigned)(1 + n_geo), LS_PP_THREADS, smem, stream, a);
+    return ls_check_launch("params_backward");
 }
 
 int64_t ls2fm_field_image_floats(const ls2fm_field_t* field, const ls2fm_radiance_t* rad) {

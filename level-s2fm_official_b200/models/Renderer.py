@@ -38,11 +38,11 @@ class Renderer:
     def _prepare(self, SDF_Field, Rad_Field=None):
         """Effective weights (weight-norm, composed radiance map) and their tensor-core operand image, built once per
         call and shared by every launch that evaluates the same parameters (sampler rounds + render forward)."""
+        from .base import prepare_params
         lib = _C.get()
-        theta = SDF_Field.SDF_MLP.theta()
-        w_eff = b_eff = rad = None
+        theta, w_eff, b_eff = prepare_params(SDF_Field.SDF_MLP, Rad_Field.Rad_dec if Rad_Field is not None else None)
+        rad = None
         if Rad_Field is not None:
-            w_eff, b_eff = Rad_Field.Rad_dec.effective_affine()
             rad = ops._rad(lib, Rad_Field.rad_spec(), w_eff.detach(), b_eff.detach(), None)
         image = ops.field_prepare_raw(lib, SDF_Field.field_spec(), SDF_Field.table().detach(), theta.detach().contiguous(), rad)
         return {"theta": theta, "w_eff": w_eff, "b_eff": b_eff, "image": image}

@@ -37,6 +37,34 @@ def effective_layers(mlp: nn.ModuleList):
     return out
 
 
+def _wn_triples(mlp: nn.ModuleList):
+    """[(weight_g, weight_v, bias)] if every layer is weight-normed, else None."""
+    out = []
+    for layer in mlp:
+        if not hasattr(layer, "weight_g"):
+            return None
+        out.append((layer.weight_g, layer.weight_v, layer.bias))
+    return out
+
+
+def prepare_params(geometry=None, radiance=None):
+    """(theta, w_eff, b_eff) of a Geometry MLP and/or a Radiance decoder.  One fused launch (ops.ParamPrep: weight norm +
+    packing + composition, with its own fused backward) when every layer is weight-normed and the decoder has the shipped
+    in -> 64 -> 64 -> 3 shape; the layer-by-layer torch path otherwise."""
+    geo = _wn_triples(geometry.mlp) if geometry is not None else []
+    rad = _wn_triples(radiance.mlp_radiance) if radiance is not None else []
+    rad_ok = radiance is None or (rad is not None and len(rad) == 3 and rad[0][1].shape[0] == 64 and
+                                  tuple(rad[1][1].shape) == (64, 64) and tuple(rad[2][1].shape) == (3, 64) and rad[0][1].shape[1] <= 68)
+    if geo is not None and rad_ok and (geo or rad):
+        flat = [t for triple in geo for t in triple] + [t for triple in (rad or []) for t in triple]
+        theta, w_eff, b_eff = ops.ParamPrep.apply(len(geo), *flat)
+        return (theta if geometry is not None else None, w_eff if radiance is not None else None,
+                b_eff if radiance is not None else None)
+    theta = ops.pack_theta(effective_layers(geometry.mlp)) if geometry is not None else None
+    w_eff, b_eff = ops.compose_affine(effective_layers(radiance.mlp_radiance)) if radiance is not None else (None, None)
+    return theta, w_eff, b_eff
+
+
 # --------------- Hash encoding (tcnn.Encoding replacement) -------------------------------
 class Encoding(nn.Module):
     """Stand-in for ``tinycudann.Encoding`` (otype Grid / type Hash / Linear interpolation) with the surface
@@ -163,7 +191,7 @@ class Geometry(nn.Module):
 
     def theta(self):
         """Packed effective parameters for the fused kernels (differentiable w.r.t. g, v, bias)."""
-        return ops.pack_theta(effective_layers(self.mlp))
+        return prepare_params(geometry=self)[0]
 
     def forward(self, points_enc):
         """Layer-by-layer evaluation of an already-built encoding (API compatibility; the hot path uses the
@@ -196,7 +224,8 @@ class Radiance(nn.Module):
         self.sigmoid = nn.Sigmoid()
 
     def effective_affine(self):
-        return ops.compose_affine(effective_layers(self.mlp_radiance))
+        _, w_eff, b_eff = prepare_params(radiance=self)
+        return w_eff, b_eff
 
     def forward(self, geo_enc):
         W, b = self.effective_affine()

@@ -465,3 +465,63 @@ class RenderLoss(torch.autograd.Function):
     def backward(ctx, g_out, _g1, _g2):
         g_rgb, g_nrm = ctx.saved_tensors
         return g_rgb * g_out, None, g_nrm * g_out, None, None
+
+
+def _param_layers(lib, layers, grads=None):
+    arr = (_C.ParamLayer * len(layers))()
+    for i, (g, v, b) in enumerate(layers):
+        arr[i].g, arr[i].v, arr[i].b = lib.ptr(g), lib.ptr(v), lib.ptr(b)
+        arr[i].dout, arr[i].din = int(v.shape[0]), int(v.shape[1])
+        if grads is not None:
+            arr[i].dg, arr[i].dv, arr[i].db = lib.ptr(grads[i][0]), lib.ptr(grads[i][1]), lib.ptr(grads[i][2])
+    return arr
+
+
+class ParamPrep(torch.autograd.Function):
+    """Weight norm of every layer + packing of the geometry MLP (theta) + composition of the radiance decoder
+    (W_eff, b_eff) in ONE launch; its backward (to every weight_g / weight_v / bias) in one more.
+
+    forward(n_geo, *tensors) with tensors = (g, v, b) per geometry layer followed by (g, v, b) of the 3 radiance layers
+    (or nothing) -> (theta, w_eff, b_eff)   (w_eff / b_eff are empty tensors without a radiance decoder)."""
+
+    @staticmethod
+    def forward(ctx, n_geo, *tensors):
+        lib = _C.get()
+        ts = [t.detach().contiguous() for t in tensors]
+        geo = [tuple(ts[3 * i:3 * i + 3]) for i in range(n_geo)]
+        rad = [tuple(ts[3 * (n_geo + i):3 * (n_geo + i) + 3]) for i in range((len(ts) - 3 * n_geo) // 3)]
+        assert len(rad) in (0, 3)
+        dev = ts[0].device
+        n_theta = sum(v.shape[0] * v.shape[1] + v.shape[0] for _, v, _ in geo)
+        theta = torch.empty(n_theta, device=dev)
+        w_eff = torch.empty(3, rad[0][1].shape[1], device=dev) if rad else torch.empty(0, device=dev)
+        b_eff = torch.empty(3, device=dev) if rad else torch.empty(0, device=dev)
+        _call(lib, "params_forward", lib.dll.ls2fm_params_forward, _param_layers(lib, geo) if geo else None, n_geo,
+              _param_layers(lib, rad) if rad else None, lib.ptr(theta), lib.ptr(w_eff), lib.ptr(b_eff), lib.stream())
+        ctx.n_geo, ctx.n_rad = n_geo, len(rad)
+        ctx.save_for_backward(*ts)
+        return theta, w_eff, b_eff
+
+    @staticmethod
+    def backward(ctx, d_theta, d_w_eff, d_b_eff):
+        lib = _C.get()
+        ts = list(ctx.saved_tensors)
+        n_geo, n_rad = ctx.n_geo, ctx.n_rad
+        grads = [torch.empty_like(t) for t in ts]
+        geo = [tuple(ts[3 * i:3 * i + 3]) for i in range(n_geo)]
+        rad = [tuple(ts[3 * (n_geo + i):3 * (n_geo + i) + 3]) for i in range(n_rad)]
+        ggeo = [tuple(grads[3 * i:3 * i + 3]) for i in range(n_geo)]
+        grad_ = [tuple(grads[3 * (n_geo + i):3 * (n_geo + i) + 3]) for i in range(n_rad)]
+        use_rad = n_rad == 3 and d_w_eff is not None and d_w_eff.numel() > 0
+        if n_rad == 3 and not use_rad:
+            for g in grads[3 * n_geo:]:
+                g.zero_()
+        if d_theta is None and n_geo:
+            d_theta = torch.zeros(sum(v.shape[0] * v.shape[1] + v.shape[0] for _, v, _ in geo), device=ts[0].device)
+        if use_rad and d_b_eff is None:
+            d_b_eff = torch.zeros(3, device=ts[0].device)
+        _call(lib, "params_backward", lib.dll.ls2fm_params_backward, _param_layers(lib, geo, ggeo) if geo else None, n_geo,
+              _param_layers(lib, rad, grad_) if use_rad else None,
+              lib.ptr(d_theta.contiguous()) if n_geo else None, lib.ptr(d_w_eff.contiguous()) if use_rad else None,
+              lib.ptr(d_b_eff.contiguous()) if use_rad else None, lib.stream())
+        return (None, *grads)

@@ -202,3 +202,30 @@ def test_fused_render_loss_matches_torch():
     assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item())
     for a, b in zip(gr, gr_ref):
         assert common.rel_err(a.cpu(), b.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("layers,dual", [((None, 64, 64, 64, 16), False), ((None, 64, 16), True)])
+def test_fused_param_prep_matches_torch_weight_norm_and_composition(layers, dual):
+    from levels2fm_b200 import ops
+    from levels2fm_b200.models import base
+    opt = common.make_opt("DTU", DEV, 16, layers, 16, dual)
+    sdf, rad, _ = common.build_models(opt)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for p in list(sdf.SDF_MLP.parameters()) + list(rad.Rad_dec.parameters()):
+            p.copy_((torch.randn(p.shape, generator=g) * 0.3 + 0.1).to(DEV))
+    theta, w_eff, b_eff = base.prepare_params(sdf.SDF_MLP, rad.Rad_dec)
+    theta_ref = ops.pack_theta(base.effective_layers(sdf.SDF_MLP.mlp))
+    w_ref, b_ref = ops.compose_affine(base.effective_layers(rad.Rad_dec.mlp_radiance))
+    assert common.rel_err(theta.cpu(), theta_ref.cpu()) < 1e-6 and common.rel_err(w_eff.cpu(), w_ref.cpu()) < 1e-5 and common.rel_err(b_eff.cpu(), b_ref.cpu()) < 1e-5
+    ct, cw, cb = torch.randn(theta.shape, generator=g).to(DEV), torch.randn(w_eff.shape, generator=g).to(DEV), torch.randn(3, generator=g).to(DEV)
+    params = list(sdf.SDF_MLP.parameters()) + list(rad.Rad_dec.parameters())
+    ours = torch.autograd.grad((theta * ct).sum() + (w_eff * cw).sum() + (b_eff * cb).sum(), params)
+    ref = torch.autograd.grad((theta_ref * ct).sum() + (w_ref * cw).sum() + (b_ref * cb).sum(), params)
+    for a, b in zip(ours, ref):
+        assert common.rel_err(a.cpu(), b.cpu()) < 2e-5, (a.shape, common.rel_err(a.cpu(), b.cpu()))
+    # geometry only / radiance only
+    assert common.rel_err(sdf.SDF_MLP.theta().cpu(), theta_ref.cpu()) < 1e-6
+    w2, b2 = rad.Rad_dec.effective_affine()
+    (w2.sum() + b2.sum()).backward()
+    assert all(p.grad is not None for p in rad.Rad_dec.parameters())
