@@ -250,6 +250,15 @@ int ls2fm_sphere_trace(const ls2fm_field_t* sdf_field, const float* ray0, const 
 int ls2fm_render_loss(const float* rgb, const float* gt, int64_t n_rays, const float* normals, int64_t n_samples,
                       float w_rgb, float w_eik, float* sums, float* g_rgb, float* g_normals, void* stream);
 
+/* ------------------------------------------------------------------ ray generation
+ * utils/camera.py:230-252 get_center_and_ray: pose [B,3,4] = [R|t] (world -> camera), kinv [B,3,3] = K^-1, pixel centres
+ * xy [N,2] shared by the B cameras -> center [B,N,3] = -R^T t, ray [B,N,3] = R^T K^-1 [x,y,1] (un-normalised).
+ * The backward accumulates (+=) the pose gradient d_pose [B,3,4] from g_center / g_ray (nullable each). */
+int ls2fm_generate_rays(const float* pose, const float* kinv, const float* xy, int32_t n_cams, int64_t n_pix,
+                        float* center, float* ray, void* stream);
+int ls2fm_generate_rays_backward(const float* pose, const float* kinv, const float* xy, int32_t n_cams, int64_t n_pix,
+                                 const float* g_center, const float* g_ray, float* d_pose, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

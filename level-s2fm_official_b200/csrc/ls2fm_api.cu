@@ -491,4 +491,28 @@ int ls2fm_render_loss(const float* rgb, const float* gt, int64_t n_rays, const f
     return ls_check_launch("render_loss");
 }
 
+int ls2fm_generate_rays(const float* pose, const float* kinv, const float* xy, int32_t n_cams, int64_t n_pix, float* center, float* ray,
+                        void* stream) {
+    if (n_cams < 0 || n_pix < 0) return ls_fail("generate_rays: bad sizes");
+    if (n_cams * n_pix > 0 && (!pose || !kinv || !xy || !center || !ray)) return ls_fail("generate_rays: NULL argument");
+    if ((int64_t)n_cams * n_pix == 0) return 0;
+    const int bs = 256;
+    LS_LAUNCH(ls_generate_rays_kernel, (unsigned)(((int64_t)n_cams * n_pix + bs - 1) / bs), bs, 0, stream, pose, kinv, xy, n_cams, n_pix,
+              center, ray);
+    return ls_check_launch("generate_rays");
+}
+
+int ls2fm_generate_rays_backward(const float* pose, const float* kinv, const float* xy, int32_t n_cams, int64_t n_pix,
+                                 const float* g_center, const float* g_ray, float* d_pose, void* stream) {
+    if (n_cams < 0 || n_pix < 0) return ls_fail("generate_rays_backward: bad sizes");
+    if (n_cams * n_pix > 0 && (!pose || !kinv || !xy || !d_pose)) return ls_fail("generate_rays_backward: NULL argument");
+    if ((int64_t)n_cams * n_pix == 0) return 0;
+    const int bs = 256;
+    int64_t gx = (n_pix + bs - 1) / bs;
+    if (gx > 64) gx = 64;
+    LS_LAUNCH(ls_generate_rays_backward_kernel, dim3((unsigned)gx, (unsigned)n_cams), bs, 0, stream, pose, kinv, xy, n_cams, n_pix, g_center,
+              g_ray, d_pose);
+    return ls_check_launch("generate_rays_backward");
+}
+
 }  // extern "C"

@@ -319,3 +319,65 @@ __global__ void ls_render_loss_kernel(const float* __restrict__ rgb, const float
         atomicAdd(sums + 1, s_eik);
     }
 }
+
+// ---------------------------------------------------------------- ray generation
+// utils/camera.py:230-252 (get_center_and_ray): grid_cam = K^-1 [x, y, 1];  world = R^T grid_cam - R^T t;  center = -R^T t;
+// ray = world - center (un-normalised, as the reference hands it to the renderer).  pose [B,3,4] = [R | t] world->camera,
+// kinv [B,3,3], xy [N,2] shared by the B cameras.  One thread per (camera, pixel).
+__global__ void ls_generate_rays_kernel(const float* __restrict__ pose, const float* __restrict__ kinv, const float* __restrict__ xy,
+                                        int n_cams, int64_t n_pix, float* __restrict__ center, float* __restrict__ ray) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)n_cams * n_pix) return;
+    const int b = (int)(gid / n_pix);
+    const int64_t n = gid - (int64_t)b * n_pix;
+    const float* P = pose + 12 * b;
+    const float* Ki = kinv + 9 * b;
+    const float x = xy[2 * n], y = xy[2 * n + 1];
+    float gc[3], tinv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) gc[i] = fmaf(Ki[3 * i], x, fmaf(Ki[3 * i + 1], y, Ki[3 * i + 2]));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tinv[j] = -(P[j] * P[3] + P[4 + j] * P[7] + P[8 + j] * P[11]);        // -R^T t
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float gw = fmaf(P[j], gc[0], fmaf(P[4 + j], gc[1], fmaf(P[8 + j], gc[2], tinv[j])));         // R^T gc + t_inv
+        center[3 * gid + j] = tinv[j];
+        ray[3 * gid + j] = gw - tinv[j];
+    }
+}
+
+// backward w.r.t. the pose: d_pose [B,3,4] += ...   (R[k][j] = P[4k + j], t[k] = P[4k + 3])
+//   ray_j = sum_k R[k][j] gc_k  (up to rounding)      -> dR[k][j] += sum_n gc_k(n) g_ray_j(n)
+//   center_j = -sum_k R[k][j] t_k                     -> dR[k][j] -= t_k sum_n g_center_j(n) ;  dt_k -= sum_j R[k][j] sum_n g_center_j(n)
+__global__ void ls_generate_rays_backward_kernel(const float* __restrict__ pose, const float* __restrict__ kinv,
+                                                 const float* __restrict__ xy, int n_cams, int64_t n_pix,
+                                                 const float* __restrict__ g_center, const float* __restrict__ g_ray,
+                                                 float* __restrict__ d_pose) {
+    const int b = blockIdx.y;
+    const float* P = pose + 12 * b;
+    const float* Ki = kinv + 9 * b;
+    float acc[12];     // [k][j] for j < 3: dR ; acc[4k+3]: dt_k
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_pix; n += (int64_t)gridDim.x * blockDim.x) {
+        const float x = xy[2 * n], y = xy[2 * n + 1];
+        float gc[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) gc[i] = fmaf(Ki[3 * i], x, fmaf(Ki[3 * i + 1], y, Ki[3 * i + 2]));
+        const int64_t o = 3 * ((int64_t)b * n_pix + n);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float gr = g_ray ? g_ray[o + j] : 0.f, gcn = g_center ? g_center[o + j] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[4 * k + j] += gc[k] * gr - P[4 * k + 3] * gcn;
+                acc[4 * k + 3] -= P[4 * k + j] * gcn;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const float v = ls_warp_sum(acc[i]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(d_pose + 12 * b + i, v);
+    }
+}

@@ -525,3 +525,29 @@ class ParamPrep(torch.autograd.Function):
               lib.ptr(d_theta.contiguous()) if n_geo else None, lib.ptr(d_w_eff.contiguous()) if use_rad else None,
               lib.ptr(d_b_eff.contiguous()) if use_rad else None, lib.stream())
         return (None, *grads)
+
+
+class GenerateRays(torch.autograd.Function):
+    """utils/camera.py:230-252 (get_center_and_ray) as one kernel: pose [B,3,4], kinv [B,3,3], xy [N,2] ->
+    center [B,N,3], ray [B,N,3]; differentiable w.r.t. the pose."""
+
+    @staticmethod
+    def forward(ctx, pose, kinv, xy):
+        lib = _C.get()
+        pose_c, kinv_c, xy_c = pose.detach().contiguous().float(), kinv.detach().contiguous().float(), xy.detach().contiguous().float()
+        B, N = pose_c.shape[0], xy_c.shape[0]
+        center = torch.empty(B, N, 3, device=pose.device)
+        ray = torch.empty(B, N, 3, device=pose.device)
+        _call(lib, "generate_rays", lib.dll.ls2fm_generate_rays, lib.ptr(pose_c), lib.ptr(kinv_c), lib.ptr(xy_c), B, N,
+              lib.ptr(center), lib.ptr(ray), lib.stream())
+        ctx.save_for_backward(pose_c, kinv_c, xy_c)
+        return center, ray
+
+    @staticmethod
+    def backward(ctx, g_center, g_ray):
+        lib = _C.get()
+        pose, kinv, xy = ctx.saved_tensors
+        d_pose = torch.zeros_like(pose)
+        _call(lib, "generate_rays_backward", lib.dll.ls2fm_generate_rays_backward, lib.ptr(pose), lib.ptr(kinv), lib.ptr(xy),
+              pose.shape[0], xy.shape[0], lib.ptr(_c(g_center)), lib.ptr(_c(g_ray)), lib.ptr(d_pose), lib.stream())
+        return d_pose, None, None

@@ -1,0 +1,27 @@
+"""Ray generation in front of the renderer (reference: utils/camera.py:230-252, the caller side of the hot path;
+SURVEY.md 8f row 2)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def mesh_grid(opt):
+    """Pixel-centre grid [H*W, 2] (x, y), utils/camera.py:253-261."""
+    y = torch.arange(opt.H, dtype=torch.float32, device=opt.device) + 0.5
+    x = torch.arange(opt.W, dtype=torch.float32, device=opt.device) + 0.5
+    Y, X = torch.meshgrid(y, x, indexing="ij")
+    return torch.stack([X, Y], dim=-1).view(-1, 2)
+
+
+def get_center_and_ray(opt, pose, intr=None, rays_idx=None, xy_grid=None):
+    """Same signature and results as the reference's get_center_and_ray: pose [B,3,4] world->camera, intr [B,3,3]
+    -> (center [B,N,3], ray [B,N,3]), rays un-normalised.  One kernel; differentiable w.r.t. the pose."""
+    assert opt.camera.model == "perspective" if hasattr(opt, "camera") else True
+    with torch.no_grad():
+        xy = mesh_grid(opt) if xy_grid is None else xy_grid[rays_idx, :]
+        kinv = intr.inverse()
+    if kinv.dim() == 2:
+        kinv = kinv[None].expand(len(pose), 3, 3)
+    return ops.GenerateRays.apply(pose, kinv, xy)

@@ -568,3 +568,24 @@ def sphere_tracing(ray0: Tensor, ray_dir: Tensor, sdf_sd, cfg: SceneCfg):
     finish = sdf_tr[:, -1, :].abs() < thr2
     return {"d_pred": d_pred, "sdf_last": sdf_tr[:, -1, 0], "finish_mask": finish, "n_iters": pts.shape[1],
             "track": pts, "acc_end": acc_e}
+
+
+# --------------------------------------------------------------------------- ray generation (caller side)
+def get_center_and_ray(pose: Tensor, intr: Tensor, xy: Tensor):
+    """utils/camera.py:230-252 (+ to_hom / img2cam / cam2world / Pose.invert, camera.py:200-217, 37-43):
+    pose [B,3,4] world->camera, intr [B,3,3], xy [N,2] pixel centres -> center [B,N,3], ray [B,N,3] (un-normalised)."""
+    B = pose.shape[0]
+    xyb = xy.repeat(B, 1, 1)
+    hom = torch.cat([xyb, torch.ones_like(xyb[..., :1])], dim=-1)
+    grid = hom @ intr.inverse().transpose(-1, -2)
+    R, t = pose[..., :3], pose[..., 3:]
+    R_inv = R.transpose(-1, -2)
+    t_inv = (-R_inv @ t)[..., 0]
+    pose_inv = torch.cat([R_inv, t_inv[..., None]], dim=-1)
+
+    def cam2world(X):
+        Xh = torch.cat([X, torch.ones_like(X[..., :1])], dim=-1)
+        return Xh @ pose_inv.transpose(-1, -2)
+    gw = cam2world(grid)
+    cw = cam2world(torch.zeros_like(grid))
+    return cw, gw - cw

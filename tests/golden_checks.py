@@ -255,3 +255,27 @@ def sphere_trace_internals(device):
     K2 = int((cnt == 0).nonzero()[0, 0])
     assert K2 == ref2["n_iters"] and 0 < K2 < 40
     assert (track[:, :K2].cpu() - ref2["track"]).abs().max().item() < 1e-4
+
+
+# ----------------------------------------------------------------------------- ray generation
+def rays_case(device, seed=0):
+    """pose gradient and values of GenerateRays vs the oracle restatement of utils/camera.py:230-252."""
+    from levels2fm_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    B, N = 3, 77
+    A = torch.randn(B, 3, 3, generator=g)
+    R, _ = torch.linalg.qr(A)
+    t = torch.randn(B, 3, generator=g)
+    pose = torch.cat([R, t[..., None]], dim=-1)
+    intr = torch.tensor([[1920.0, 0.0, 800.0], [0.0, 1900.0, 600.0], [0.0, 0.0, 1.0]]).repeat(B, 1, 1)
+    xy = torch.rand(N, 2, generator=g) * torch.tensor([1600.0, 1200.0])
+    wc, wr = torch.randn(B, N, 3, generator=g), torch.randn(B, N, 3, generator=g)
+    p_ref = pose.clone().requires_grad_(True)
+    c_ref, r_ref = port.get_center_and_ray(p_ref, intr, xy)
+    ((c_ref * wc).sum() + (r_ref * wr).sum()).backward()
+    p = pose.clone().to(device).requires_grad_(True)
+    c, r = ops.GenerateRays.apply(p, intr.inverse().to(device), xy.to(device))
+    ((c * wc.to(device)).sum() + (r * wr.to(device)).sum()).backward()
+    assert_close(c, c_ref, tol=1e-5, what="ray centers")
+    assert_close(r, r_ref, tol=1e-5, what="ray directions")
+    assert_close(p.grad, p_ref.grad, tol=1e-4, what="pose gradient")

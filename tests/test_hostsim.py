@@ -140,3 +140,7 @@ def test_fused_param_prep_matches_torch_weight_norm_and_composition(layers, dual
     w2, b2 = rad.Rad_dec.effective_affine()
     (w2.sum() + b2.sum()).backward()
     assert all(p.grad is not None for p in rad.Rad_dec.parameters())
+
+
+def test_ray_generation_kernel_matches_oracle():
+    gc.rays_case("cpu")
