@@ -300,8 +300,17 @@ int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, c
     const int smem = net.total * (int)sizeof(float);
     if (smem > ls_max_smem() || (field->n_levels & 3))     // operands too large / level groups not chunk-aligned: SIMT kernel
         return ls2fm_field_forward_simt(field, pts, rad, out_y, out_sdf, out_nrm, out_rgb, stream);
-    if (ls_opt_in_smem(ls_field_forward_tc_kernel, smem)) return 1;
     const int64_t n_tiles = (pts->n + LS_TC_M - 1) / LS_TC_M;
+    if (!rad && !out_nrm) {      // values only: the two-tiles-in-flight kernel, weights without their transposed copies
+        const LsTcNet cnet = ls_plan_tc(*field, 0, false);
+        const int csmem = cnet.total * (int)sizeof(float);
+        if (ls_opt_in_smem(ls_field_sdf_tc_kernel, csmem)) return 1;
+        const int64_t n_pairs = (n_tiles + 1) / 2;
+        const int64_t grid = n_pairs < ls_sm_count() ? n_pairs : ls_sm_count();
+        LS_LAUNCH(ls_field_sdf_tc_kernel, (unsigned)grid, LS_TC_THREADS, csmem, stream, a, cnet, net);
+        return ls_check_launch("field_forward(sdf)");
+    }
+    if (ls_opt_in_smem(ls_field_forward_tc_kernel, smem)) return 1;
     int64_t grid = n_tiles < ls_sm_count() ? n_tiles : ls_sm_count();
     LS_LAUNCH(ls_field_forward_tc_kernel, (unsigned)grid, LS_TC_THREADS, smem, stream, a, net);
     return ls_check_launch("field_forward");

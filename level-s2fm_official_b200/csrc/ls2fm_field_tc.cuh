@@ -37,7 +37,9 @@ struct LsTcNet {
 
 inline int ls_round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-inline LsTcNet ls_plan_tc(const ls2fm_field_t& f, int rad_in_dim) {
+// with_transposed = false: the values-only kernel keeps no W^T copies and no reduction scratch (about half the shared
+// memory, which the hardware hands to L1 -- the coarse grid levels then stay L1-resident)
+inline LsTcNet ls_plan_tc(const ls2fm_field_t& f, int rad_in_dim, bool with_transposed = true) {
     LsTcNet n;
     memset(&n, 0, sizeof(n));
     const int K = f.n_layers;
@@ -49,7 +51,7 @@ inline LsTcNet ls_plan_tc(const ls2fm_field_t& f, int rad_in_dim) {
         n.n_in_pad[l] = l == 0 ? ls_round_up(f.dims[0], 16) : LS_H;
         n.w_hi[l] = off; off += n.n_out_pad[l] * n.k_in_pad[l];
         n.w_lo[l] = off; off += n.n_out_pad[l] * n.k_in_pad[l];
-        if (!last) {
+        if (!last && with_transposed) {
             n.wt_hi[l] = off; off += n.n_in_pad[l] * LS_H;
             n.wt_lo[l] = off; off += n.n_in_pad[l] * LS_H;
         }
@@ -59,13 +61,13 @@ inline LsTcNet ls_plan_tc(const ls2fm_field_t& f, int rad_in_dim) {
     n.rad_pitch = ls_round4(rad_in_dim > 0 ? rad_in_dim : 4);
     n.weff = off; off += 3 * n.rad_pitch + 4;
     n.misc = ls_round4(off); off = n.misc + 8;
-    n.red = off; off += 2 * 4 * LS_TC_M * 3;
+    n.red = off; off += with_transposed ? 2 * 4 * LS_TC_M * 3 : 0;
     n.total = off;
     return n;
 }
 
 // weights -> shared memory operands (hi/lo, K-major no-swizzle), zero padded
-LS_DEV void ls_stage_weights_tc(const LsFieldArgs& a, const LsTcNet& net, float* smem, int tid, int nt) {
+LS_DEV void ls_stage_weights_tc(const LsFieldArgs& a, const LsTcNet& net, float* smem, int tid, int nt, bool with_transposed = true) {
     const int K = a.f.n_layers;
     for (int l = 0; l < K; ++l) {
         const int din = a.f.dims[l], dout = a.f.dims[l + 1];
@@ -89,7 +91,7 @@ LS_DEV void ls_stage_weights_tc(const LsFieldArgs& a, const LsTcNet& net, float*
             smem[net.w_hi[l] + o] = hi;
             smem[net.w_lo[l] + o] = lo;
         }
-        if (l < K - 1) {
+        if (l < K - 1 && with_transposed) {
             const int Nt = net.n_in_pad[l];
             for (int e = tid; e < Nt * LS_H; e += nt) {
                 const int i = e / LS_H, j = e - i * LS_H;
@@ -181,8 +183,8 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int l = 4 * cg + r;
-                float h[2] = {0.f, 0.f}, dh[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-                if (l < L) ls_level_eval(a.f, l, u, h, dh);
+                float h[2], dh[2][3];
+                ls_level_eval(a.f, l, u, h, dh);        // L % 4 == 0 on this path: all four levels of the group exist
                 e8[2 * r] = h[0]; e8[2 * r + 1] = h[1];
 #pragma unroll
                 for (int fi = 0; fi < 2; ++fi)
@@ -383,6 +385,149 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
                 }
             }
         }
+    }
+    ls_tc_dealloc(tmem);
+}
+
+// ================================================================ SDF-only forward, two tiles in flight
+// The sampler rounds, sphere tracing and SDF.infer_sdf need only y (no normals, no radiance): nothing has to survive the
+// layer that consumes it, so a tile needs 192 TMEM columns (operand hi/lo 128 + accumulator 64) and TWO tiles fit.  All 512
+// threads run one instruction stream that alternates between the two tiles: while the tensor core works on a batch of tile A
+// the threads gather / run the epilogue of tile B, so the MMA round trips that serialise the one-tile kernel are hidden.
+struct LsSdfTile {
+    int64_t i;          // output index of this thread's sample
+    bool valid;
+    int col;            // TMEM column base of the tile context: [col, +64) operand hi, [col+64, +64) lo, [col+128, +64) accumulator
+};
+
+// net: compact plan (no W^T); img: the full plan the operand image was built with
+__global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_sdf_tc_kernel(const LsFieldArgs a, const LsTcNet net, const LsTcNet img) {
+    LS_DYN_SMEM(smem);
+    if (ls_n_samples(a.p) == 0) return;
+    const int t = threadIdx.x;
+    const int cg = t >> 7;
+    const int row = ls_tc_row();
+    const int K = a.f.n_layers, H = K - 1, L = a.f.n_levels;
+    const int dout = a.f.dims[K], nh = a.f.dims[0] - 3;
+    const float sp_beta = a.f.softplus_beta, sp_thr = a.f.softplus_threshold, inv_beta = 1.f / a.f.softplus_beta;
+    if (a.f.tc_image) {      // copy W_l (hi | lo, contiguous) and the biases of every layer out of the full image
+        for (int l = 0; l < K; ++l) {
+            const int nw4 = (2 * net.n_out_pad[l] * net.k_in_pad[l]) / 4;
+            const float4* src = reinterpret_cast<const float4*>(a.f.tc_image + img.w_hi[l]);
+            float4* dst = reinterpret_cast<float4*>(smem + net.w_hi[l]);
+            for (int e = threadIdx.x; e < nw4; e += blockDim.x) dst[e] = __ldg(src + e);
+            for (int e = threadIdx.x; e < LS_H; e += blockDim.x) smem[net.bias[l] + e] = __ldg(a.f.tc_image + img.bias[l] + e);
+        }
+    } else {
+        ls_stage_weights_tc(a, net, smem, threadIdx.x, blockDim.x, false);
+    }
+    ls_fence_smem_to_async();
+    LsTcBar* bar0 = reinterpret_cast<LsTcBar*>(smem + net.misc);
+    LsTcBar* bar1 = reinterpret_cast<LsTcBar*>(smem + net.misc + 2);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(smem + net.misc + 4);
+    const uint32_t tmem = ls_tc_alloc(slot);
+    ls_tc_bar_init(bar0);
+    ls_tc_bar_init(bar1);
+    uint32_t ph[2] = {0, 0};
+
+    const int64_t n_pts = ls_n_samples(a.p);
+    const int64_t n_tiles = (n_pts + LS_TC_M - 1) / LS_TC_M;
+    const int64_t n_pairs = (n_tiles + 1) / 2;
+
+    // gather of one tile into its operand columns
+    auto gather = [&](LsSdfTile& T, int64_t tile) {
+        const int64_t i_in = tile * LS_TC_M + row;
+        T.valid = tile < n_tiles && i_in < n_pts;
+        T.i = i_in;
+        float x[3] = {0.f, 0.f, 0.f}, u[3];
+        int ray_id = 0;
+        if (T.valid) ls_sample_point(a.p, i_in, x, &ray_id, &T.i);
+        ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
+        if (4 * cg < L) {
+            float e8[8], hi[8], lo[8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int l = 4 * cg + r;
+                float h[2], dh[2][3];
+                ls_level_eval(a.f, l, u, h, dh);        // L % 4 == 0 on this path: all four levels of the group exist
+                e8[2 * r] = h[0]; e8[2 * r + 1] = h[1];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ls_split_tf32(e8[q], hi[q], lo[q]);
+            ls_tmem_st(tmem, T.col + 8 * cg, hi, 8);
+            ls_tmem_st(tmem, T.col + 64 + 8 * cg, lo, 8);
+        }
+        if (cg == 0) {
+            float e8[8] = {ls_fdiv(x[0], a.f.rescale), ls_fdiv(x[1], a.f.rescale), ls_fdiv(x[2], a.f.rescale), 1.f, 0.f, 0.f, 0.f, 0.f};
+            float hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ls_split_tf32(e8[q], hi[q], lo[q]);
+            ls_tmem_st(tmem, T.col + nh, hi, 8);
+            ls_tmem_st(tmem, T.col + 64 + nh, lo, 8);
+        }
+    };
+    // issue the MMA batch of layer l (l == H: output layer) for a tile; every thread passes the barrier inside
+    auto issue = [&](const LsSdfTile& T, int l, LsTcBar* bar) {
+        ls_tc_sync_before_mma();
+        if (t == 0) {
+            ls_tc_mma_x3(tmem, T.col + 128, T.col, T.col + 64, smem + net.w_hi[l], smem + net.w_lo[l], l == H ? 32 : LS_H, net.k_in_pad[l]);
+            ls_tc_commit(bar);
+        }
+    };
+    // epilogue of hidden layer l: accumulator slice -> bias + softplus -> operand slice of the next layer
+    auto epilogue = [&](const LsSdfTile& T, int l) {
+        const float* bias = smem + net.bias[l] + 16 * cg;
+        float v[16], hi[16], lo[16];
+        ls_tmem_ld(tmem, T.col + 128 + 16 * cg, v, 16);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float z = l == 0 ? v[q] : v[q] + bias[q];
+            ls_split_tf32(ls_softplus_fast(z, sp_beta, inv_beta, sp_thr), hi[q], lo[q]);
+        }
+        ls_tmem_st(tmem, T.col + 16 * cg, hi, 16);
+        ls_tmem_st(tmem, T.col + 64 + 16 * cg, lo, 16);
+    };
+    auto output = [&](const LsSdfTile& T) {
+        const float* bias = smem + net.bias[K - 1];
+        if (cg == 0) {
+            float y[16];
+            ls_tmem_ld(tmem, T.col + 128, y, 16);
+            if (T.valid) {
+                if (a.out_sdf) a.out_sdf[T.i] = a.s * (y[0] + bias[0]);
+                if (a.out_y) {
+#pragma unroll
+                    for (int o = 0; o < 16; ++o) if (o < dout) a.out_y[T.i * dout + o] = y[o] + bias[o];
+                }
+            }
+        } else if (cg == 1 && a.out_y && dout > 16) {
+            float y[8];
+            ls_tmem_ld(tmem, T.col + 128 + 16, y, 8);
+            if (T.valid) {
+#pragma unroll
+                for (int o = 0; o < 8; ++o) if (16 + o < dout) a.out_y[T.i * dout + 16 + o] = y[o] + bias[16 + o];
+            }
+        }
+    };
+
+    LsSdfTile A, B;
+    A.col = 0; B.col = 192;
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        gather(A, 2 * pair);
+        issue(A, 0, bar0);
+        gather(B, 2 * pair + 1);
+        issue(B, 0, bar1);
+        for (int l = 0; l < H; ++l) {
+            ls_tc_wait(bar0, ph[0]);
+            epilogue(A, l);
+            issue(A, l + 1, bar0);
+            ls_tc_wait(bar1, ph[1]);
+            epilogue(B, l);
+            issue(B, l + 1, bar1);
+        }
+        ls_tc_wait(bar0, ph[0]);
+        output(A);
+        ls_tc_wait(bar1, ph[1]);
+        output(B);
     }
     ls_tc_dealloc(tmem);
 }
