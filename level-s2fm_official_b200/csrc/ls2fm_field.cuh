@@ -595,9 +595,7 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
             ls_el(P, LS_H, o, s8) = v;
         }
         // ------------------------------------------------ B2: gather, e and (TAN) edot = Je nbar
-        // (unrolled: the 32 corner loads of the four levels are independent and should all be in flight together --
-        //  the gather is L2-latency bound with two warps per scheduler)
-#pragma unroll
+#pragma unroll 1
         for (int r = 0; r < 4; ++r) {
             const int l = g + 4 * r;
             if (l < L) {
