@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 RAYS_PER_GPU = 4096
+WORKLOAD_TRACE = [False]      # set when the workload includes the per-iteration sphere_tracing call (c4)
 GRID_BYTES_PER_EVAL = {16: 1024, 4: 256}     # L * 8 corners * F=2 * 4 B  
 
 
@@ -36,6 +37,9 @@ def workload_opt(name: str, device: str):
         over.update({"SDF.VolSDF.volsdf_sampling": True, "SDF.VolSDF.sample_intvs": 64, "SDF.VolSDF.final_sample_intvs": 64})
     elif name == "uniform128":
         over.update({"SDF.VolSDF.volsdf_sampling": False, "SDF.VolSDF.sample_intvs": 128})
+    elif name == "c4":      # the reference's shipped DTU configuration + the sphere-tracing call CameraSet.render makes per iteration
+        over = {"SDF.arch.layers": [None, 64, 16], "RadF.arch.layers": [None, 64, 64, 3],
+                "SDF.VolSDF.volsdf_sampling": False, "SDF.VolSDF.sample_intvs": 128}
     else:
         raise ValueError(name)
     return default_opt("DTU", device=device, **over)
@@ -45,6 +49,8 @@ WORKLOAD_DESC = {
     "c2": "BASELINE configs[1]: 4096 rays, error-bounded sampler (64 coarse + 64 fine = 128 samples/ray), L=16 hash grid, "
           "SDF MLP 35-64-64-64-17, RadF 49-64-64-3, fused fwd+bwd, DTU bounds",
     "uniform128": "4096 rays, 128 uniform samples/ray, L=16 hash grid, SDF MLP 35-64-64-64-17, RadF 49-64-64-3, fused fwd+bwd, DTU bounds",
+    "c4": "BASELINE configs[3] shape: 4096 rays, 128 uniform samples/ray, L=16 hash grid, shipped SDF MLP 35-64-17, RadF 49-64-64-3, "
+          "one sphere_tracing call on all rays per iteration (pipelines/Camera.py:506), fused fwd+bwd, DTU bounds",
 }
 
 
@@ -96,8 +102,8 @@ class ClockSampler:
 def oracle_setup(workload: str, n_rays: int, seed: int = 0):
     from levels2fm_b200 import synthetic
     from oracle import port
-    cfg = port.SceneCfg(n_levels=16, sdf_layers=(None, 64, 64, 64, 16), rad_layers=(None, 64, 64, 3),
-                        sample_intvs=64 if workload == "c2" else 128, final_sample_intvs=64,
+    cfg = port.SceneCfg(n_levels=16, sdf_layers=(None, 64, 16) if workload == "c4" else (None, 64, 64, 64, 16),
+                        rad_layers=(None, 64, 64, 3), sample_intvs=64 if workload == "c2" else 128, final_sample_intvs=64,
                         volsdf_sampling=workload == "c2", iters_max_st=10)
     sdf_sd, rad_sd = port.random_state(cfg, seed=0, table_std=1e-4, generic_weights=False, sphere_bias=0.5)
     for sd in (sdf_sd, rad_sd):
@@ -116,6 +122,9 @@ def oracle_step(cfg, sdf_sd, rad_sd, center, ray, gt):
             v.grad = None
     out = port.render_forward(center, ray, sdf_sd, rad_sd, cfg)
     loss = synthetic.render_loss(out, gt)
+    if len(cfg.sdf_layers) == 3 and not cfg.volsdf_sampling and cfg.sample_intvs == 128 and getattr(cfg, "_trace", True) and WORKLOAD_TRACE[0]:
+        st = port.sphere_tracing(center, ray, sdf_sd, cfg)
+        loss = loss + 1e-2 * (st["d_pred"] - out["depth_mlp"][..., 0].detach()).abs().mean()
     loss.backward()
     return float(loss.detach())
 
@@ -124,6 +133,7 @@ def cpu_baseline(workload: str, budget_s: float = 12.0, n_rays: int = 128):
     """The oracle port (reference algorithm restated in eager PyTorch, CPU) on a bounded sample of the workload."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    WORKLOAD_TRACE[0] = workload == "c4"
     st = oracle_setup(workload, n_rays)
     oracle_step(*st)                                   # warm-up
     t0, n = time.perf_counter(), 0
@@ -144,6 +154,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n_rays = 128
+    WORKLOAD_TRACE[0] = args.workload == "c4"
     st = oracle_setup(args.workload, n_rays)
     for _ in range(max(args.warmup, 1)):
         oracle_step(*st)
@@ -213,6 +224,9 @@ def main():
         bucket.zero()
         out = ren.forward(opt, c, r, sdf, rad)
         loss = synthetic.render_loss_fused(out, g)
+        if args.workload == "c4":      # depth-consistency term between the sphere-traced and the volume-rendered depth
+            d_pred, _, _, _ = sdf.sphere_tracing(c, r, sdf)
+            loss = loss + 1e-2 * (d_pred - out["depth_mlp"][..., 0].detach()).abs().mean()
         loss.backward()
         bucket.allreduce()
         return loss, out
