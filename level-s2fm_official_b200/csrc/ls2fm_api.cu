@@ -7,6 +7,7 @@
 
 #include "ls2fm_field.cuh"
 #include "ls2fm_field_tc.cuh"
+#include "ls2fm_field_bwtc.cuh"
 #include "ls2fm_render.cuh"
 #include "ls2fm_sampler.cuh"
 #include "ls2fm_trace.cuh"
@@ -240,7 +241,7 @@ int ls2fm_params_backward(const ls2fm_param_layer_t* geo, int32_t n_geo, const l
 
 int64_t ls2fm_field_image_floats(const ls2fm_field_t* field, const ls2fm_radiance_t* rad) {
     if (!field || field->n_layers < 2 || field->n_layers > LS2FM_MAX_LAYERS) return -1;
-    return (int64_t)ls_plan_tc(*field, rad ? rad->in_dim : 0).misc;
+    return (int64_t)ls_plan_tc(*field, rad ? rad->in_dim : 0).image_total;
 }
 
 int ls2fm_field_prepare(const ls2fm_field_t* field, const ls2fm_radiance_t* rad, float* image, void* stream) {
@@ -316,17 +317,16 @@ int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, c
     return ls_check_launch("field_forward");
 }
 
-int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
-                         const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
-                         const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
-                         void* stream) {
+static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
+                                  const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
+                                  const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
+                                  void* stream, bool allow_tc) {
     if (ls_check_field(field) || ls_check_points(pts)) return 1;
     if (pts->n == 0) return 0;
     if (rad && ls_check_rad(rad, field, pts)) return 1;
     if (pts->ray_index || pts->n_active || pts->out_stride) return ls_fail("field_backward: compacted ray lists are forward-only");
     if (rad && g_rgb && (!saved_nrm || !saved_rgb)) return ls_fail("field_backward: saved_nrm / saved_rgb required with radiance");
     if (!rad && (g_rgb || d_w_eff || d_b_eff || d_geo2)) return ls_fail("field_backward: radiance gradients need the radiance block");
-    if (pts->n == 0) return 0;
     LsFieldArgs a;
     ls_fill_args(a, field, pts, (rad && g_rgb) ? rad : nullptr);
     a.g_y = g_y; a.g_sdf = g_sdf; a.g_nrm = g_nrm; a.g_rgb = g_rgb;
@@ -334,6 +334,29 @@ int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, 
     a.d_table = d_table; a.d_theta = d_theta; a.d_w_eff = d_w_eff; a.d_b_eff = d_b_eff; a.d_geo2 = d_geo2;
     const bool with_rad = rad && g_rgb;
     const bool tan = with_rad || g_nrm;
+    const int KL = field->n_layers;
+    // ---- tensor-core kernel: needs the operand image (weights stream from it), the 2-channel form (normals carry gradient),
+    //      chunk-aligned level groups and matrices that fit a ring slot; everything else runs the fp32-SIMT kernel below
+    if (allow_tc && tan && field->tc_image && (field->n_levels & 3) == 0) {
+        const LsTcNet img = ls_plan_tc(*field, with_rad ? rad->in_dim : 0);
+        const LsBtNet net = ls_plan_bt(*field, with_rad ? rad->in_dim : 0);
+        const int smem = net.total * (int)sizeof(float);
+        bool fits = smem <= ls_max_smem() && img.k_in_pad[0] <= LS_BT_EROWS && img.n_in_pad[0] <= LS_BT_EROWS;
+        for (int l = 0; l < KL - 1; ++l) fits = fits && 2 * img.n_out_pad[l] * img.k_in_pad[l] <= LS_BT_SLOT && 2 * img.n_in_pad[l] * LS_H <= LS_BT_SLOT;
+        if (fits) {
+            a.net = ls_plan_net(*field, with_rad ? rad->in_dim : 0, 1, false);        // theta offsets
+            const int64_t n_tiles = (pts->n + LS_BT_TILE - 1) / LS_BT_TILE;
+            const int64_t grid = n_tiles < ls_sm_count() ? n_tiles : ls_sm_count();
+#define LS_BT_LAUNCH(KV)                                                                                   \
+            do {                                                                                           \
+                if (ls_opt_in_smem(ls_field_backward_tc_kernel<KV>, smem)) return 1;                       \
+                LS_LAUNCH((ls_field_backward_tc_kernel<KV>), (unsigned)grid, LS_BT_THREADS, smem, stream, a, img, net); \
+            } while (0)
+            if (KL == 2) LS_BT_LAUNCH(2); else if (KL == 3) LS_BT_LAUNCH(3); else LS_BT_LAUNCH(4);
+#undef LS_BT_LAUNCH
+            return ls_check_launch("field_backward(tc)");
+        }
+    }
     a.net = ls_plan_net(*field, with_rad ? rad->in_dim : 0, LS_BW_WARPS, true);
     const int smem = a.net.total * (int)sizeof(float);
     if (smem > ls_max_smem()) return ls_fail("field_backward: network does not fit in shared memory");
@@ -344,11 +367,26 @@ int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, 
         if (ls_opt_in_smem(ls_field_backward_kernel<TANV, KV>, smem)) return 1;                         \
         LS_LAUNCH((ls_field_backward_kernel<TANV, KV>), (unsigned)grid, LS_BW_THREADS, smem, stream, a); \
     } while (0)
-    const int KL = field->n_layers;
     if (tan) { if (KL == 2) LS_BW_LAUNCH(true, 2); else if (KL == 3) LS_BW_LAUNCH(true, 3); else LS_BW_LAUNCH(true, 4); }
     else { if (KL == 2) LS_BW_LAUNCH(false, 2); else if (KL == 3) LS_BW_LAUNCH(false, 3); else LS_BW_LAUNCH(false, 4); }
 #undef LS_BW_LAUNCH
     return ls_check_launch("field_backward");
+}
+
+int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
+                         const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
+                         const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
+                         void* stream) {
+    return ls_field_backward_impl(field, pts, rad, g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb, d_table, d_theta, d_w_eff, d_b_eff,
+                                  d_geo2, stream, true);
+}
+
+int ls2fm_field_backward_simt(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
+                              const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
+                              const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
+                              void* stream) {
+    return ls_field_backward_impl(field, pts, rad, g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb, d_table, d_theta, d_w_eff, d_b_eff,
+                                  d_geo2, stream, false);
 }
 
 int ls2fm_composite_forward(const float* ray, const float* t, const float* sdf, const float* rgbs, const float* nrm,

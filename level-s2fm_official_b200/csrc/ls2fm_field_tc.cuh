@@ -33,6 +33,10 @@ struct LsTcNet {
     int misc;            // mbarrier + tmem slot
     int red;             // [4][128][3] x 2 cross-column-group reduction scratch (normal, colour)
     int total;           // floats
+    // image-only extension (global memory, never part of the forward kernels' shared-memory copy): the output layer as a
+    // transposed operand B[n = hidden unit][k = output], hi then lo, for the reverse pass of the tensor-core backward kernel
+    int wtl_hi, wtl_lo, kl_pad;
+    int image_total;     // floats of the operand image
 };
 
 inline int ls_round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -63,6 +67,10 @@ inline LsTcNet ls_plan_tc(const ls2fm_field_t& f, int rad_in_dim, bool with_tran
     n.misc = ls_round4(off); off = n.misc + 8;
     n.red = off; off += with_transposed ? 2 * 4 * LS_TC_M * 3 : 0;
     n.total = off;
+    n.kl_pad = ls_round_up(f.dims[K], 8);
+    n.wtl_hi = ls_round4(n.weff + 3 * ls_round4(LS2FM_MAX_RAD_IN) + 4) + 16;     // independent of the radiance block the image was built with
+    n.wtl_lo = n.wtl_hi + LS_H * n.kl_pad;
+    n.image_total = n.wtl_lo + LS_H * n.kl_pad;
     return n;
 }
 
@@ -125,7 +133,19 @@ LS_DEV void ls_stage_weights_tc(const LsFieldArgs& a, const LsTcNet& net, float*
 
 // builds the operand image in global memory (same layout as the kernel's shared memory, floats [0, net.misc))
 __global__ void ls_field_prepare_kernel(const LsFieldArgs a, const LsTcNet net, float* __restrict__ image) {
-    ls_stage_weights_tc(a, net, image, (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)(gridDim.x * blockDim.x));
+    const int tid = (int)(blockIdx.x * blockDim.x + threadIdx.x), nt = (int)(gridDim.x * blockDim.x);
+    ls_stage_weights_tc(a, net, image, tid, nt);
+    // extension: W_{K-1} as B[n = i][k = o] (K-major, rows o >= dout zero)
+    const int K = a.f.n_layers, dout = a.f.dims[K], kl = net.kl_pad;
+    const float* G = a.f.theta + a.net.gw_off[K - 1];           // Wt [64][dout]
+    for (int e = tid; e < LS_H * kl; e += nt) {
+        const int i = e / kl, o = e - i * kl;
+        float hi, lo;
+        ls_split_tf32(o < dout ? __ldg(G + i * dout + o) : 0.f, hi, lo);
+        const int off = ls_op_off(i, o, LS_H) >> 2;
+        image[net.wtl_hi + off] = hi;
+        image[net.wtl_lo + off] = lo;
+    }
 }
 
 // fast softplus for the tensor-core epilogue: ex2/lg2 based (MUFU rate), absolute error ~1e-9 at beta = 100

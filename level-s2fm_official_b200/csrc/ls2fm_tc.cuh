@@ -74,6 +74,10 @@ LS_DEV void ls_tc_wait(LsTcBar*, uint32_t& phase) { __syncthreads(); phase ^= 1;
 LS_DEV float ls_tf32_lo(float x) { return x - ls_tf32_trunc(x); }
 LS_DEV void ls_split_tf32(float v, float& hi, float& lo) { hi = ls_tf32_round(v); lo = v - hi; }
 LS_DEV void ls_fence_smem_to_async() {}
+// bulk global -> shared copy completing on an mbarrier (emulated: plain copy at issue time, waits are no-ops)
+LS_DEV void ls_bar_init1(LsTcBar* b) { b->arrived = 0; }
+LS_DEV void ls_bulk_g2s(float* dst, const float* src, int bytes, LsTcBar*) { memcpy(dst, src, (size_t)bytes); }
+LS_DEV void ls_bar_wait(LsTcBar*, uint32_t) {}
 #else
 // ------------------------------------------------------------------------------------------------ sm_100a
 struct LsTcBar { unsigned long long v; };
@@ -186,6 +190,23 @@ LS_DEV void ls_split_tf32(float v, float& hi, float& lo) {
     lo = v - hi;
 }
 LS_DEV void ls_fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// ---- bulk (TMA 1-D) global -> shared copy completing on an mbarrier; all three are called by ONE thread
+LS_DEV void ls_bar_init1(LsTcBar* b) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(ls_smem_u32(b)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n");
+}
+// bytes % 16 == 0, dst / src 16-byte aligned.  The barrier's phase completes when all bytes have landed.
+LS_DEV void ls_bulk_g2s(float* dst, const float* src, int bytes, LsTcBar* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(ls_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(ls_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ls_smem_u32(bar)) : "memory");
+}
+LS_DEV void ls_bar_wait(LsTcBar* b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(ls_smem_u32(b)), "r"(parity) : "memory");
+}
 #endif
 
 // 3xTF32 product by the issuing thread: D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi (small terms first)

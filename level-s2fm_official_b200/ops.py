@@ -223,9 +223,10 @@ def field_forward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: O
 
 def field_backward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: Optional[_C.Radiance],
                        g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb,
-                       d_table, d_theta, d_w_eff=None, d_b_eff=None, d_geo2=None):
-    f = spec.c_field(lib, table, theta)
-    _call(lib, "field_backward", lib.dll.ls2fm_field_backward, f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
+                       d_table, d_theta, d_w_eff=None, d_b_eff=None, d_geo2=None, image=None, simt=False):
+    """image: the operand image of field_prepare_raw for the SAME theta -- with it the tensor-core backward kernel runs."""
+    f = spec.c_field(lib, table, theta, image)
+    _call(lib, "field_backward_simt" if simt else "field_backward", lib.dll.ls2fm_field_backward_simt if simt else lib.dll.ls2fm_field_backward, f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
         lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), lib.stream())
 
 
@@ -292,6 +293,8 @@ def composite_backward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, 
 
 
 # ------------------------------------------------------------------------- autograd
+BACKWARD_SIMT = False      # tests flip this to cross-check the tensor-core backward kernel against the fp32-SIMT one
+
 def _c(t):
     return None if t is None else t.contiguous()
 
@@ -324,6 +327,7 @@ class FieldEval(torch.autograd.Function):
         ctx.spec, ctx.rad_spec = spec, rad_spec
         ctx.pt_args = (t_offset, n_per_ray)
         ctx.with_rad, ctx.want_y, ctx.want_nrm = with_rad, want_y, want_nrm
+        ctx.image = image
         ctx.save_for_backward(table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, nrm if with_rad else None, rgb)
         out_y = y if want_y else table.new_empty(0)
         out_nrm = nrm if (want_nrm or with_rad) else table.new_empty(0)
@@ -349,7 +353,7 @@ class FieldEval(torch.autograd.Function):
         d_b = torch.zeros_like(b_eff) if with_rad else None
         d_geo2 = torch.empty_like(geo2) if (with_rad and geo2 is not None) else None
         field_backward_raw(lib, spec, table, theta, pts, rad, g_y, g_sdf, g_nrm, g_rgb, s_nrm, s_rgb,
-                           d_table, d_theta, d_w, d_b, d_geo2)
+                           d_table, d_theta, d_w, d_b, d_geo2, image=ctx.image, simt=BACKWARD_SIMT)
         return (None, None, d_table, d_theta, d_w, d_b, d_geo2, None, None, None, None, None, None, None, None, None)
 
 

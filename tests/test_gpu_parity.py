@@ -74,6 +74,29 @@ def test_render_forward_backward_matches_oracle(dataset, n_levels, layers, n_sam
         assert common.rel_err(a, b) < 2e-3, (k, common.rel_err(a, b))
 
 
+@pytest.mark.parametrize("dataset,n_levels,layers,n_samples,n_rays,dual", [
+    ("DTU", 16, (None, 64, 64, 64, 16), 128, 300, False),       # config 2 networks; 76 800 samples: every CTA walks several tiles
+    ("bmvs", 16, (None, 64, 16), 47, 33, True),                 # dual field, ragged tile tail
+    ("DTU", 4, (None, 64, 16), 64, 16, False),
+])
+def test_tensor_core_backward_matches_simt_backward(dataset, n_levels, layers, n_samples, n_rays, dual):
+    """ls2fm_field_backward (tcgen05: 2-channel stacked tiles, streamed weights, all weight gradients in TMEM) against
+    ls2fm_field_backward_simt (fp32 FMA pipes) on identical inputs: both are 'fp32-level', so they agree to ~1e-5."""
+    from levels2fm_b200 import ops
+    res = {}
+    for simt in (True, False):
+        ops.BACKWARD_SIMT = simt
+        try:
+            opt = common.make_opt(dataset, DEV, n_levels, layers, n_samples, dual)
+            _, res[simt] = common.render_parity_case(opt, n_levels, 2, n_rays, device=DEV)
+        finally:
+            ops.BACKWARD_SIMT = False
+    for k in res[True]:
+        a, b = res[False][k][0], res[True][k][0]
+        assert common.cosine(a, b) > 1 - 1e-9, (k, common.cosine(a, b))
+        assert common.rel_err(a, b) < 2e-4, (k, common.rel_err(a, b))
+
+
 def test_golden_c1_render():
     gold = gc.load("c1_render.npz")
     out, grads, loss = gc.run_c1_product(gold, DEV)

@@ -55,6 +55,22 @@ def test_render_forward_backward_matches_oracle(dataset, n_levels, layers, n_sam
         assert common.rel_err(a, b) < 2e-3, (k, common.rel_err(a, b))
 
 
+def test_tensor_core_backward_agrees_with_simt_backward():
+    """same sources under the emulator: the tcgen05 backward kernel (emulated TMEM / MMA / bulk copies) vs the SIMT one."""
+    from levels2fm_b200 import ops
+    res = {}
+    for simt in (True, False):
+        ops.BACKWARD_SIMT = simt
+        try:
+            opt = common.make_opt("DTU", "cpu", 16, (None, 64, 64, 16), 21, False)
+            _, res[simt] = common.render_parity_case(opt, 16, 2, 5)
+        finally:
+            ops.BACKWARD_SIMT = False
+    for k in res[True]:
+        a, b = res[False][k][0], res[True][k][0]
+        assert common.rel_err(a, b) < 5e-5, (k, common.rel_err(a, b))
+
+
 def test_golden_c1_through_kernels():
     gold = gc.load("c1_render.npz")
     out, grads, loss = gc.run_c1_product(gold, "cpu")
