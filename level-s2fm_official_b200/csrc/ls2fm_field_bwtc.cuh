@@ -86,12 +86,30 @@ LS_DEV void ls_bt_matrix(const LsTcNet& img, int H, int b, int* src, int* floats
 // weight-gradient batch: D[m][d_col + n] += sum_r A(m, r) B(n, r) over the tile's 128 rows, 3xTF32 (raw = hi by truncation)
 LS_DEV void ls_bt_wgrad(uint32_t tmem, int d_col, const float* a_raw, const float* a_lo, int a_lbo, const float* b_raw, const float* b_lo,
                         int b_lbo, int N) {
+#if defined(LS_HOSTSIM)
     for (int ks = 0; ks < LS_BT_KG / 2; ++ks) {      // 8 rows (two groups of 4) per MMA
         const int ao = ks * 2 * (a_lbo / 4), bo = ks * 2 * (b_lbo / 4);
         ls_tc_mma_ss(tmem, d_col, a_lo + ao, a_lbo, b_raw + bo, b_lbo, N, true);
         ls_tc_mma_ss(tmem, d_col, a_raw + ao, a_lbo, b_lo + bo, b_lbo, N, true);
         ls_tc_mma_ss(tmem, d_col, a_raw + ao, a_lbo, b_raw + bo, b_lbo, N, true);
     }
+#else
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(LS_TC_M >> 4) << 24);
+    uint64_t ar = ls_tc_desc(ls_smem_u32(a_raw), (uint32_t)a_lbo, 128), al = ls_tc_desc(ls_smem_u32(a_lo), (uint32_t)a_lbo, 128);
+    uint64_t br = ls_tc_desc(ls_smem_u32(b_raw), (uint32_t)b_lbo, 128), bl = ls_tc_desc(ls_smem_u32(b_lo), (uint32_t)b_lbo, 128);
+    const uint64_t as = (uint64_t)(2 * a_lbo >> 4), bs = (uint64_t)(2 * b_lbo >> 4);     // 8 rows (two groups of 4) per MMA
+    const uint32_t d = tmem + (uint32_t)d_col;
+#define LS_BT_SS(A, B) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" \
+                                    :: "r"(d), "l"(A), "l"(B), "r"(idesc))
+#pragma unroll
+    for (int ks = 0; ks < LS_BT_KG / 2; ++ks) {
+        LS_BT_SS(al, br);
+        LS_BT_SS(ar, bl);
+        LS_BT_SS(ar, br);
+        ar += as; al += as; br += bs; bl += bs;
+    }
+#undef LS_BT_SS
+#endif
 }
 
 template <int K>
@@ -132,12 +150,15 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     LsTcBar* bar = reinterpret_cast<LsTcBar*>(smem + net.misc);
     LsTcBar* full0 = reinterpret_cast<LsTcBar*>(smem + net.misc + 2);
     LsTcBar* full1 = reinterpret_cast<LsTcBar*>(smem + net.misc + 4);
+    LsTcBar* bar2 = reinterpret_cast<LsTcBar*>(smem + net.misc + 6);     // weight-gradient batches (off the critical path)
     const uint32_t tmem = ls_tc_alloc(reinterpret_cast<uint32_t*>(smem + net.misc + 8));
     ls_tc_bar_init(bar);
+    ls_tc_bar_init(bar2);
     if (t == 0) { ls_bar_init1(full0); ls_bar_init1(full1); }
     ls_fence_smem_to_async();
     __syncthreads();
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase2 = 0;
+    bool wg_pending = false;            // a weight-gradient batch may still be reading the staging arrays / the stash
     {   // zero the weight-gradient accumulators (every lane: the upper 64 are scratch of the M = 128 instruction shape)
         float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -156,7 +177,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         }
     };
     if (t == 0) { ring_fetch(0); ring_fetch(1); }
-    // thread 0, after the barrier of batch g: wait for its matrix; returns the slot
+    // warp 0, after the barrier of batch g: wait for its matrix; returns the slot
     auto ring_slot = [&](int64_t g) -> const float* {
         ls_bar_wait((g & 1) ? full1 : full0, (uint32_t)((g >> 1) & 1));
         return smem + net.ring + (int)(g & 1) * LS_BT_SLOT;
@@ -164,7 +185,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     // all threads: wait for batch g, then thread 0 refills its slot with the matrix of batch g + 2
     auto batch_done = [&]() {
         ls_tc_wait(bar, phase);
-        if (t == 0) ring_fetch(gb + 2);
+        if (warp == 0) { if (ls_elect()) ring_fetch(gb + 2); }
         ++gb;
     };
     // persistent accumulators
@@ -172,26 +193,16 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
 #pragma unroll
     for (int l = 0; l < LS2FM_MAX_LAYERS; ++l) bacc[l] = 0.f;
     float weff_acc = 0.f;
-    const int bj = t & 63, bpart = t >> 6;          // bias sums: feature bj, primal row groups 2 bpart, 2 bpart + 1
-    auto bias_sum = [&](int n_rows) -> float {      // sum over the tile's primal rows of staged adjoint feature bj
-        float s = 0.f;
-        if (bj < n_rows) {
+    float blast[8];                     // output-layer bias gradient: this thread's 8 columns of ybar, summed over its tiles
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int pg = 2 * bpart + h;
-                const int grp = (pg >> 2) * 8 + (pg & 3);      // groups whose rows have (row & 16) == 0
-                const float4 v = ls_ld4(ZR + grp * LS_BT_LBOF + bj * 4);
-                s += (v.x + v.y) + (v.z + v.w);
-            }
-        }
-        return s;
-    };
+    for (int k = 0; k < 8; ++k) blast[k] = 0.f;
     const int st_off = (row >> 2) * LS_BT_LBOF + (row & 3);        // + feature * 4
     const int st_off_e = (row >> 2) * LS_BT_LBOF_E + (row & 3);
     const int colE = LS_BT_A + 64 * (H - 1);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ------------------------------------------------ B1: upstream gradients of this thread's sample
+        if (wg_pending) { ls_tc_wait(bar2, phase2); wg_pending = false; }    // the stash / staging arrays are rewritten below
         const int64_t i_in = tile * LS_BT_TILE + sl;
         const bool valid = i_in < a.p.n;
         float x[3] = {0.f, 0.f, 0.f}, u[3];
@@ -317,11 +328,13 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         for (int l = 0; l < H; ++l) {
             const int a_col = l == 0 ? colE : LS_BT_A + 64 * (l - 1);
             ls_tc_sync_before_mma();
-            if (t == 0) {
+            if (warp == 0) {
                 const float* W = ring_slot(gb);
                 const int Kp = img.k_in_pad[l];
-                ls_tc_mma_x3(tmem, LS_BT_D, a_col, LS_BT_LO, W, W + LS_H * Kp, LS_H, Kp);
-                ls_tc_commit(bar);
+                if (ls_elect()) {
+                    ls_tc_mma_x3(tmem, LS_BT_D, a_col, LS_BT_LO, W, W + LS_H * Kp, LS_H, Kp);
+                    ls_tc_commit(bar);
+                }
             }
             batch_done();
             // epilogue: the primal lane takes columns 0..7 of the pair's 16, the tangent lane 8..15 (both channels of those)
@@ -384,6 +397,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                 }
                 c8[k] = v;
                 lo8[k] = ls_tf32_lo(v);
+                if (!isT) blast[k] += v;
                 ZR[st_off + o * 4] = v;
                 ZL[st_off + o * 4] = lo8[k];
             }
@@ -398,15 +412,19 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
             }
             ls_fence_smem_to_async();
             ls_tc_sync_before_mma();
-            if (t == 0) {
+            if (warp == 0) {
                 const float* W = ring_slot(gb);
-                // output-layer weight gradient, transposed: D[i][o] += sum_r a_H[r][i] ybar'[r][o]   (columns dout..dout+2: G[c][i])
-                ls_bt_wgrad(tmem, LS_BT_WG, AR, AL, LS_BT_LBO, ZR, ZL, LS_BT_LBO, 32);
-                ls_tc_mma_x3(tmem, LS_BT_D, LS_BT_LO, LS_BT_LO + 32, W, W + LS_H * img.kl_pad, LS_H, img.kl_pad);
-                ls_tc_commit(bar);
+                if (ls_elect()) {
+                    // critical path first: the product into the layer below ...
+                    ls_tc_mma_x3(tmem, LS_BT_D, LS_BT_LO, LS_BT_LO + 32, W, W + LS_H * img.kl_pad, LS_H, img.kl_pad);
+                    ls_tc_commit(bar);
+                    // ... then the output-layer weight gradient, transposed: D[i][o] += sum_r a_H[r][i] ybar'[r][o] (columns
+                    // dout..dout+2: G[c][i]); it runs under the next epilogue and is only waited for before the staging arrays change
+                    ls_bt_wgrad(tmem, LS_BT_WG, AR, AL, LS_BT_LBO, ZR, ZL, LS_BT_LBO, 32);
+                    ls_tc_commit(bar2);
+                }
             }
-            bacc[K - 1] += bias_sum(32);
-            __syncthreads();                 // every reader of the staged rows is done before anybody can pass the wait and restage
+            wg_pending = true;
             batch_done();
         }
         // ------------------------------------------------ B6: reverse through the hidden layers, k = H .. 1
@@ -438,16 +456,41 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                 out[8 + c] = isT ? zd[c] : r;
             }
 #pragma unroll
+            for (int c = 0; c < 16; ++c) lo[c] = ls_tf32_lo(out[c]);
+            ls_tmem_st(tmem, colA + 16 * cg, out, 16);
+            ls_tmem_st(tmem, LS_BT_LO + 16 * cg, lo, 16);
+            if (k > 1) {
+                // bias gradient of layer k-1 = column sums of zbar_k over the primal rows: recursive halving over the 16 primal lanes
+                // of the warp (15 shuffles), lane l ends with column 16 cg + (l & 15) of this warp's rows
+                float w8[8], w4[4], w2[2];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float r = __shfl_xor_sync(0xffffffffu, (lane & 8) ? out[c] : out[8 + c], 8);
+                    w8[c] = ((lane & 8) ? out[8 + c] : out[c]) + r;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float r = __shfl_xor_sync(0xffffffffu, (lane & 4) ? w8[c] : w8[4 + c], 4);
+                    w4[c] = ((lane & 4) ? w8[4 + c] : w8[c]) + r;
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float r = __shfl_xor_sync(0xffffffffu, (lane & 2) ? w4[c] : w4[2 + c], 2);
+                    w2[c] = ((lane & 2) ? w4[2 + c] : w4[c]) + r;
+                }
+                const float r = __shfl_xor_sync(0xffffffffu, (lane & 1) ? w2[0] : w2[1], 1);
+                if (!isT) bacc[k - 1] += ((lane & 1) ? w2[1] : w2[0]) + r;
+            }
+            float ap[16];
+            if (k > 1) ls_tmem_ld(tmem, colA - 64 + 16 * cg, ap, 16);
+            // the previous weight-gradient batch still reads the staging arrays: everything above ran under it
+            ls_tc_wait(bar2, phase2);
+#pragma unroll
             for (int c = 0; c < 16; ++c) {
-                lo[c] = ls_tf32_lo(out[c]);
                 ZR[st_off + (16 * cg + c) * 4] = out[c];
                 ZL[st_off + (16 * cg + c) * 4] = lo[c];
             }
-            ls_tmem_st(tmem, colA + 16 * cg, out, 16);
-            ls_tmem_st(tmem, LS_BT_LO + 16 * cg, lo, 16);
             if (k > 1) {        // input of layer k-1: a_{k-1} stack
-                float ap[16];
-                ls_tmem_ld(tmem, colA - 64 + 16 * cg, ap, 16);
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     AR[st_off + (16 * cg + c) * 4] = ap[c];
@@ -462,20 +505,22 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
             }
             ls_fence_smem_to_async();
             ls_tc_sync_before_mma();
-            if (t == 0) {
+            if (warp == 0) {
                 const float* W = ring_slot(gb);
-                if (k > 1) {
-                    ls_bt_wgrad(tmem, LS_BT_WG + 64 * (k - 1), ZR, ZL, LS_BT_LBO, AR, AL, LS_BT_LBO, LS_H);
-                    ls_tc_mma_x3(tmem, LS_BT_D, colA, LS_BT_LO, W, W + LS_H * LS_H, LS_H, LS_H);
-                } else {
-                    ls_bt_wgrad(tmem, LS_BT_WG + 24, ZR, ZL, LS_BT_LBO, ES, AL, LS_BT_LBO_E, LS_BT_EROWS);
-                    const int N0 = img.n_in_pad[0];
-                    ls_tc_mma_x3(tmem, LS_BT_D, colA, LS_BT_LO, W, W + N0 * LS_H, N0, LS_H);
+                if (ls_elect()) {
+                    if (k > 1) {
+                        ls_tc_mma_x3(tmem, LS_BT_D, colA, LS_BT_LO, W, W + LS_H * LS_H, LS_H, LS_H);
+                        ls_tc_commit(bar);
+                        ls_bt_wgrad(tmem, LS_BT_WG + 64 * (k - 1), ZR, ZL, LS_BT_LBO, AR, AL, LS_BT_LBO, LS_H);
+                    } else {
+                        const int N0 = img.n_in_pad[0];
+                        ls_tc_mma_x3(tmem, LS_BT_D, colA, LS_BT_LO, W, W + N0 * LS_H, N0, LS_H);
+                        ls_tc_commit(bar);
+                        ls_bt_wgrad(tmem, LS_BT_WG + 24, ZR, ZL, LS_BT_LBO, ES, AL, LS_BT_LBO_E, LS_BT_EROWS);
+                    }
+                    ls_tc_commit(bar2);
                 }
-                ls_tc_commit(bar);
             }
-            if (k > 1) bacc[k - 1] += bias_sum(LS_H);
-            __syncthreads();
             batch_done();
         }
         // ------------------------------------------------ B7: hash-table gradient scatter (this thread's two levels)
@@ -521,6 +566,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     }
 
     // ------------------------------------------------ flush the parameter gradients
+    if (wg_pending) ls_tc_wait(bar2, phase2);
     ls_tc_sync_before_mma();
     if (a.d_theta && my_tiles > 0) {
         float* GS = smem + net.gs;
@@ -556,11 +602,19 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                 }
             }
         }
+        // bias gradients.  Hidden layers: primal lane l of every warp holds the column 16 cg + (l & 15) partial of its 16 rows.
 #pragma unroll
-        for (int l = 1; l < K; ++l) {
-            const int n_out = a.f.dims[l + 1];
-            // combine the 8 row-group partials of feature bj through the atomics themselves
-            if (bj < n_out) atomicAdd(a.d_theta + a.net.gb_off[l] + bj, bacc[l]);
+        for (int l = 1; l < K - 1; ++l)
+            if (!isT) atomicAdd(a.d_theta + a.net.gb_off[l] + 16 * cg + (lane & 15), bacc[l]);
+        // output layer: 8 columns per thread, summed over the warp's primal lanes first
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = blast[k];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            if (lane == 0 && 8 * cg + k < dout) atomicAdd(a.d_theta + a.net.gb_off[K - 1] + 8 * cg + k, v);
         }
         __syncthreads();
         if (rad && a.d_w_eff && t < 3 * kg) {      // geo block of dL/dW_eff: sum_i W_last[1+k][i] G[c][i] + b_last[1+k] sum_s pbar[c]

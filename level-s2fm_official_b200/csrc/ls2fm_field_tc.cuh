@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
         for (int l = 0; l < H; ++l) {
             const int a_hi = l == 0 ? colE_hi : (l - 1) * 128, a_lo = a_hi + 64;
             ls_tc_sync_before_mma();
-            if (t == 0) {
+            if ((t >> 5) == 0 && ls_elect()) {      // one lane of a converged warp: uniform-register descriptors, back-to-back MMAs
                 ls_tc_mma_x3(tmem, colD, a_hi, a_lo, smem + net.w_hi[l], smem + net.w_lo[l], LS_H, net.k_in_pad[l]);
                 ls_tc_commit(bar);
             }
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
         float y[16];
         {
             ls_tc_sync_before_mma();
-            if (t == 0) {
+            if ((t >> 5) == 0 && ls_elect()) {      // one lane of a converged warp: uniform-register descriptors, back-to-back MMAs
                 ls_tc_mma_x3(tmem, colD, (H - 1) * 128, (H - 1) * 128 + 64, smem + net.w_hi[K - 1], smem + net.w_lo[K - 1], 32, LS_H);
                 ls_tc_commit(bar);
             }
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
             }
             for (int l = H - 1; l >= 0; --l) {
                 ls_tc_sync_before_mma();
-                if (t == 0) {
+                if ((t >> 5) == 0 && ls_elect()) {      // one lane of a converged warp: uniform-register descriptors, back-to-back MMAs
                     ls_tc_mma_x3(tmem, colD, l * 128, l * 128 + 64, smem + net.wt_hi[l], smem + net.wt_lo[l], net.n_in_pad[l], LS_H);
                     ls_tc_commit(bar);
                 }
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_sdf_tc_kernel(const
     // issue the MMA batch of layer l (l == H: output layer) for a tile; every thread passes the barrier inside
     auto issue = [&](const LsSdfTile& T, int l, LsTcBar* bar) {
         ls_tc_sync_before_mma();
-        if (t == 0) {
+        if ((t >> 5) == 0 && ls_elect()) {      // one lane of a converged warp: uniform-register descriptors, back-to-back MMAs
             ls_tc_mma_x3(tmem, T.col + 128, T.col, T.col + 64, smem + net.w_hi[l], smem + net.w_lo[l], l == H ? 32 : LS_H, net.k_in_pad[l]);
             ls_tc_commit(bar);
         }

@@ -71,6 +71,7 @@ LS_DEV void ls_tc_mma_ss(uint32_t, int d_col, const float* A, int a_lbo, const f
 }
 LS_DEV void ls_tc_commit(LsTcBar* b) { b->arrived += 1; }
 LS_DEV void ls_tc_wait(LsTcBar*, uint32_t& phase) { __syncthreads(); phase ^= 1; }
+LS_DEV bool ls_elect() { return (threadIdx.x & 31) == 0; }
 LS_DEV float ls_tf32_lo(float x) { return x - ls_tf32_trunc(x); }
 LS_DEV void ls_split_tf32(float v, float& hi, float& lo) { hi = ls_tf32_round(v); lo = v - hi; }
 LS_DEV void ls_fence_smem_to_async() {}
@@ -150,15 +151,27 @@ LS_DEV void ls_tc_sync_before_mma() {
 LS_DEV uint64_t ls_tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46);
 }
+// One lane of a converged warp.  MMA issue belongs inside   if (warp == W) { ...; if (ls_elect()) { issue; commit; } }   : under
+// elect.sync the compiler keeps descriptors in uniform registers and emits back-to-back UTCHMMA; under  if (tid == 0)  it wraps
+// every MMA in a 10-instruction R2UR waterfall (measured: ~50 cycles per MMA of pure issue).
+LS_DEV bool ls_elect() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(p));
+    return p != 0;
+}
 // D[:, d_col + n] (+)= sum_k A[:, a_col + k] * B[n][k]; A from TMEM, B K-major no-swizzle in smem; N % 16 == 0, K % 8 == 0
 LS_DEV void ls_tc_mma(uint32_t tmem, int d_col, int a_col, const float* B, int N, int K, bool accumulate) {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(LS_TC_M >> 4) << 24);
-    const uint32_t b0 = ls_smem_u32(B);
+    uint64_t bdesc = ls_tc_desc(ls_smem_u32(B), N * 16, 128);
+    const uint64_t bstep = (uint64_t)(2 * N);          // one K = 8 step = two 4-column groups of N rows x 16 B, in 16-byte units
+    uint32_t a = tmem + (uint32_t)a_col;
+    const uint32_t d = tmem + (uint32_t)d_col;
     for (int kb = 0; kb < K / 8; ++kb) {
-        const uint64_t bdesc = ls_tc_desc(b0 + kb * 2 * (N * 16), N * 16, 128);
         const uint32_t acc = (accumulate || kb > 0) ? 1u : 0u;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
-                     :: "r"(tmem + (uint32_t)d_col), "r"(tmem + (uint32_t)(a_col + kb * 8)), "l"(bdesc), "r"(idesc), "r"(acc));
+                     :: "r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc));
+        bdesc += bstep;                                 // (only the 14-bit start-address field moves; it cannot carry out)
+        a += 8;
     }
 }
 // one K = 8 step with BOTH operands in shared memory (K-major, SBO = 128 B, per-operand LBO)
