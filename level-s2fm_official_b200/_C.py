@@ -85,6 +85,7 @@ SIGNATURES = {
     "ls2fm_field_forward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),
     "ls2fm_field_backward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),
+    "ls2fm_field_backward_tc": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),
     "ls2fm_composite_forward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 5),
     "ls2fm_composite_backward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 9),
     "ls2fm_sample_uniform": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _F3, _F3, _VP, _VP, _VP]),

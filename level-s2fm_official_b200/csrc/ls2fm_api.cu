@@ -320,7 +320,7 @@ int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, c
 static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
                                   const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
                                   const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
-                                  void* stream, bool allow_tc) {
+                                  void* stream, int mode /* 0 auto, 1 simt, 2 tensor core or fail */) {
     if (ls_check_field(field) || ls_check_points(pts)) return 1;
     if (pts->n == 0) return 0;
     if (rad && ls_check_rad(rad, field, pts)) return 1;
@@ -337,7 +337,11 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
     const int KL = field->n_layers;
     // ---- tensor-core kernel: needs the operand image (weights stream from it), the 2-channel form (normals carry gradient),
     //      chunk-aligned level groups and matrices that fit a ring slot; everything else runs the fp32-SIMT kernel below
-    if (allow_tc && tan && field->tc_image && (field->n_levels & 3) == 0) {
+    //      Its weight gradients round the layer inputs to tf32 (2^-12 relative, unbiased, per term of a sum over all rows), which
+    //      only averages out over many rows: launches below LS_BT_MIN_SAMPLES stay on the exact kernel (they are latency-bound anyway).
+    const bool tc_ok = tan && field->tc_image && (field->n_levels & 3) == 0;
+    if (mode == 2 && !tc_ok) return ls_fail("field_backward_tc: needs field.tc_image, a gradient on the normals and n_levels % 4 == 0");
+    if ((mode == 2 || (mode == 0 && pts->n >= LS_BT_MIN_SAMPLES)) && tc_ok) {
         const LsTcNet img = ls_plan_tc(*field, with_rad ? rad->in_dim : 0);
         const LsBtNet net = ls_plan_bt(*field, with_rad ? rad->in_dim : 0);
         const int smem = net.total * (int)sizeof(float);
@@ -356,6 +360,7 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
 #undef LS_BT_LAUNCH
             return ls_check_launch("field_backward(tc)");
         }
+        if (mode == 2) return ls_fail("field_backward_tc: the network does not fit the tensor-core kernel");
     }
     a.net = ls_plan_net(*field, with_rad ? rad->in_dim : 0, LS_BW_WARPS, true);
     const int smem = a.net.total * (int)sizeof(float);
@@ -378,7 +383,7 @@ int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, 
                          const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
                          void* stream) {
     return ls_field_backward_impl(field, pts, rad, g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb, d_table, d_theta, d_w_eff, d_b_eff,
-                                  d_geo2, stream, true);
+                                  d_geo2, stream, 0);
 }
 
 int ls2fm_field_backward_simt(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
@@ -386,7 +391,15 @@ int ls2fm_field_backward_simt(const ls2fm_field_t* field, const ls2fm_points_t* 
                               const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
                               void* stream) {
     return ls_field_backward_impl(field, pts, rad, g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb, d_table, d_theta, d_w_eff, d_b_eff,
-                                  d_geo2, stream, false);
+                                  d_geo2, stream, 1);
+}
+
+int ls2fm_field_backward_tc(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
+                            const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
+                            const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
+                            void* stream) {
+    return ls_field_backward_impl(field, pts, rad, g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb, d_table, d_theta, d_w_eff, d_b_eff,
+                                  d_geo2, stream, 2);
 }
 
 int ls2fm_composite_forward(const float* ray, const float* t, const float* sdf, const float* rgbs, const float* nrm,

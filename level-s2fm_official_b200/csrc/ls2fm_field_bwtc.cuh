@@ -32,6 +32,7 @@
 
 constexpr int LS_BT_THREADS = 512;
 constexpr int LS_BT_TILE = 64;                  // samples per tile
+constexpr int64_t LS_BT_MIN_SAMPLES = 32768;    // automatic dispatch: smaller launches run the exact fp32-SIMT kernel
 constexpr int LS_BT_KG = 32;                    // groups of 4 rows in a staging array (128 rows)
 constexpr int LS_BT_LBO = LS_H * 16 + 16;       // bytes between row groups of a 64-feature staging array (+16: conflict-free stores)
 constexpr int LS_BT_LBOF = LS_BT_LBO / 4;       // ... in floats (260)
@@ -46,7 +47,7 @@ constexpr int LS_BT_LO = 384;
 constexpr int LS_BT_D = 448;
 
 struct LsBtNet {         // shared-memory plan (float offsets)
-    int zr, zl, ar, al;  // staging: adjoint raw / lo, layer-input raw / lo           [32 groups][64 features][4 rows] padded
+    int zr, zl, ar;      // staging: adjoint raw / lo, layer input (tf32-rounded)    [32 groups][64 features][4 rows] padded
     int es;              // encoding stash (raw), operand of the layer-0 weight gradient [32 groups][48 features][4 rows] padded
     int ring;            // 2 slots
     int bias[LS2FM_MAX_LAYERS];
@@ -64,7 +65,6 @@ inline LsBtNet ls_plan_bt(const ls2fm_field_t& f, int rad_in_dim) {
     n.zr = off; off += stage;
     n.zl = off; off += stage;
     n.ar = off; off += stage;
-    n.al = off; off += stage;
     n.es = off; off += LS_BT_KG * LS_BT_LBOF_E;
     n.ring = off; off += 2 * LS_BT_SLOT;         // also absorbs the M = 128 over-read of the arrays above
     for (int l = 0; l < f.n_layers; ++l) { n.bias[l] = off; off += LS_H; }
@@ -83,30 +83,36 @@ LS_DEV void ls_bt_matrix(const LsTcNet& img, int H, int b, int* src, int* floats
     else { const int l = 2 * H - b; *src = img.wt_hi[l]; *floats = 2 * img.n_in_pad[l] * LS_H; }
 }
 
-// weight-gradient batch: D[m][d_col + n] += sum_r A(m, r) B(n, r) over the tile's 128 rows, 3xTF32 (raw = hi by truncation)
-LS_DEV void ls_bt_wgrad(uint32_t tmem, int d_col, const float* a_raw, const float* a_lo, int a_lbo, const float* b_raw, const float* b_lo,
-                        int b_lbo, int N) {
+// weight-gradient batch: D[m][d_col + n] += sum_r A(m, r) B(n, r) over the tile's 128 rows.  One operand ("split": the adjoint) is
+// exact as raw + lo (raw read as tf32 by truncation); the other ("single": the layer input) was rounded to tf32 (rna) when it was
+// staged -- an unbiased 2^-12 relative perturbation of each term of a sum over >= thousands of rows, far below the fp32 atomics'
+// own reordering noise.  split_is_a: the split operand is A (M = its features), else B.
+LS_DEV void ls_bt_wgrad(uint32_t tmem, int d_col, const float* p_raw, const float* p_lo, int p_lbo, const float* s_hi, int s_lbo, int N,
+                        bool split_is_a) {
 #if defined(LS_HOSTSIM)
     for (int ks = 0; ks < LS_BT_KG / 2; ++ks) {      // 8 rows (two groups of 4) per MMA
-        const int ao = ks * 2 * (a_lbo / 4), bo = ks * 2 * (b_lbo / 4);
-        ls_tc_mma_ss(tmem, d_col, a_lo + ao, a_lbo, b_raw + bo, b_lbo, N, true);
-        ls_tc_mma_ss(tmem, d_col, a_raw + ao, a_lbo, b_lo + bo, b_lbo, N, true);
-        ls_tc_mma_ss(tmem, d_col, a_raw + ao, a_lbo, b_raw + bo, b_lbo, N, true);
+        const int po = ks * 2 * (p_lbo / 4), so = ks * 2 * (s_lbo / 4);
+        if (split_is_a) {
+            ls_tc_mma_ss(tmem, d_col, p_lo + po, p_lbo, s_hi + so, s_lbo, N, true);
+            ls_tc_mma_ss(tmem, d_col, p_raw + po, p_lbo, s_hi + so, s_lbo, N, true);
+        } else {
+            ls_tc_mma_ss(tmem, d_col, s_hi + so, s_lbo, p_lo + po, p_lbo, N, true);
+            ls_tc_mma_ss(tmem, d_col, s_hi + so, s_lbo, p_raw + po, p_lbo, N, true);
+        }
     }
 #else
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(LS_TC_M >> 4) << 24);
-    uint64_t ar = ls_tc_desc(ls_smem_u32(a_raw), (uint32_t)a_lbo, 128), al = ls_tc_desc(ls_smem_u32(a_lo), (uint32_t)a_lbo, 128);
-    uint64_t br = ls_tc_desc(ls_smem_u32(b_raw), (uint32_t)b_lbo, 128), bl = ls_tc_desc(ls_smem_u32(b_lo), (uint32_t)b_lbo, 128);
-    const uint64_t as = (uint64_t)(2 * a_lbo >> 4), bs = (uint64_t)(2 * b_lbo >> 4);     // 8 rows (two groups of 4) per MMA
+    uint64_t pr = ls_tc_desc(ls_smem_u32(p_raw), (uint32_t)p_lbo, 128), pl = ls_tc_desc(ls_smem_u32(p_lo), (uint32_t)p_lbo, 128);
+    uint64_t sh = ls_tc_desc(ls_smem_u32(s_hi), (uint32_t)s_lbo, 128);
+    const uint64_t ps = (uint64_t)(2 * p_lbo >> 4), ss = (uint64_t)(2 * s_lbo >> 4);     // 8 rows (two groups of 4) per MMA
     const uint32_t d = tmem + (uint32_t)d_col;
 #define LS_BT_SS(A, B) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" \
                                     :: "r"(d), "l"(A), "l"(B), "r"(idesc))
 #pragma unroll
     for (int ks = 0; ks < LS_BT_KG / 2; ++ks) {
-        LS_BT_SS(al, br);
-        LS_BT_SS(ar, bl);
-        LS_BT_SS(ar, br);
-        ar += as; al += as; br += bs; bl += bs;
+        if (split_is_a) { LS_BT_SS(pl, sh); LS_BT_SS(pr, sh); }
+        else { LS_BT_SS(sh, pl); LS_BT_SS(sh, pr); }
+        pr += ps; pl += ps; sh += ss;
     }
 #undef LS_BT_SS
 #endif
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     const int RP = net.rad_pitch;
     const int nin = rad ? a.r.in_dim - kg : 0;      // radiance inputs that are not geo features: x, n, dir, Fourier, (geo2)
     const float* Weff = smem + net.weff;
-    float* ZR = smem + net.zr; float* ZL = smem + net.zl; float* AR = smem + net.ar; float* AL = smem + net.al;
+    float* ZR = smem + net.zr; float* ZL = smem + net.zl; float* AR = smem + net.ar;
     float* ES = smem + net.es;
     float* RIN = ZR;                                // [64][nin] radiance inputs of the tile (dead before the staging arrays are written)
     float* PB = ZL;                                 // [64][4]  radiance pre-activation gradients
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 lo8[k] = ls_tf32_lo(c8[k]);
-                ES[st_off_e + (8 * cg + k) * 4] = c8[k];
+                ES[st_off_e + (8 * cg + k) * 4] = ls_tf32_rna(c8[k]);
             }
             ls_tmem_st(tmem, colE + 8 * cg, c8, 8);
             ls_tmem_st(tmem, LS_BT_LO + 8 * cg, lo8, 8);
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 lo8[k] = ls_tf32_lo(c8[k]);
-                ES[st_off_e + (nh + k) * 4] = c8[k];
+                ES[st_off_e + (nh + k) * 4] = ls_tf32_rna(c8[k]);
             }
             ls_tmem_st(tmem, colE + nh, c8, 8);
             ls_tmem_st(tmem, LS_BT_LO + nh, lo8, 8);
@@ -407,8 +413,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
             ls_tmem_ld(tmem, LS_BT_A + 64 * (H - 1) + 16 * cg, ah, 16);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                AR[st_off + (16 * cg + k) * 4] = ah[k];
-                AL[st_off + (16 * cg + k) * 4] = ls_tf32_lo(ah[k]);
+                AR[st_off + (16 * cg + k) * 4] = ls_tf32_rna(ah[k]);
             }
             ls_fence_smem_to_async();
             ls_tc_sync_before_mma();
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                     ls_tc_commit(bar);
                     // ... then the output-layer weight gradient, transposed: D[i][o] += sum_r a_H[r][i] ybar'[r][o] (columns
                     // dout..dout+2: G[c][i]); it runs under the next epilogue and is only waited for before the staging arrays change
-                    ls_bt_wgrad(tmem, LS_BT_WG, AR, AL, LS_BT_LBO, ZR, ZL, LS_BT_LBO, 32);
+                    ls_bt_wgrad(tmem, LS_BT_WG, ZR, ZL, LS_BT_LBO, AR, LS_BT_LBO, 32, false);
                     ls_tc_commit(bar2);
                 }
             }
@@ -493,14 +498,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
             if (k > 1) {        // input of layer k-1: a_{k-1} stack
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    AR[st_off + (16 * cg + c) * 4] = ap[c];
-                    AL[st_off + (16 * cg + c) * 4] = ls_tf32_lo(ap[c]);
-                }
-            } else {            // input of layer 0: the stash is the raw operand, its lo part goes to AL (stash layout)
-#pragma unroll
-                for (int c = 0; c < LS_BT_EROWS / 4; ++c) {
-                    const int f = (LS_BT_EROWS / 4) * cg + c;
-                    AL[st_off_e + f * 4] = ls_tf32_lo(ES[st_off_e + f * 4]);
+                    AR[st_off + (16 * cg + c) * 4] = ls_tf32_rna(ap[c]);
                 }
             }
             ls_fence_smem_to_async();
@@ -511,12 +509,12 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                     if (k > 1) {
                         ls_tc_mma_x3(tmem, LS_BT_D, colA, LS_BT_LO, W, W + LS_H * LS_H, LS_H, LS_H);
                         ls_tc_commit(bar);
-                        ls_bt_wgrad(tmem, LS_BT_WG + 64 * (k - 1), ZR, ZL, LS_BT_LBO, AR, AL, LS_BT_LBO, LS_H);
+                        ls_bt_wgrad(tmem, LS_BT_WG + 64 * (k - 1), ZR, ZL, LS_BT_LBO, AR, LS_BT_LBO, LS_H, true);
                     } else {
                         const int N0 = img.n_in_pad[0];
                         ls_tc_mma_x3(tmem, LS_BT_D, colA, LS_BT_LO, W, W + N0 * LS_H, N0, LS_H);
                         ls_tc_commit(bar);
-                        ls_bt_wgrad(tmem, LS_BT_WG + 24, ZR, ZL, LS_BT_LBO, ES, AL, LS_BT_LBO_E, LS_BT_EROWS);
+                        ls_bt_wgrad(tmem, LS_BT_WG + 24, ZR, ZL, LS_BT_LBO, ES, LS_BT_LBO_E, LS_BT_EROWS, true);
                     }
                     ls_tc_commit(bar2);
                 }

@@ -74,6 +74,7 @@ LS_DEV void ls_tc_wait(LsTcBar*, uint32_t& phase) { __syncthreads(); phase ^= 1;
 LS_DEV bool ls_elect() { return (threadIdx.x & 31) == 0; }
 LS_DEV float ls_tf32_lo(float x) { return x - ls_tf32_trunc(x); }
 LS_DEV void ls_split_tf32(float v, float& hi, float& lo) { hi = ls_tf32_round(v); lo = v - hi; }
+LS_DEV float ls_tf32_rna(float v) { return ls_tf32_round(v); }
 LS_DEV void ls_fence_smem_to_async() {}
 // bulk global -> shared copy completing on an mbarrier (emulated: plain copy at issue time, waits are no-ops)
 LS_DEV void ls_bar_init1(LsTcBar* b) { b->arrived = 0; }
@@ -201,6 +202,11 @@ LS_DEV void ls_split_tf32(float v, float& hi, float& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
     hi = __uint_as_float(hb);
     lo = v - hi;
+}
+LS_DEV float ls_tf32_rna(float v) {
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    return __uint_as_float(hb);
 }
 LS_DEV void ls_fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 // ---- bulk (TMA 1-D) global -> shared copy completing on an mbarrier; all three are called by ONE thread

@@ -223,10 +223,14 @@ def field_forward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: O
 
 def field_backward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: Optional[_C.Radiance],
                        g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb,
-                       d_table, d_theta, d_w_eff=None, d_b_eff=None, d_geo2=None, image=None, simt=False):
-    """image: the operand image of field_prepare_raw for the SAME theta -- with it the tensor-core backward kernel runs."""
+                       d_table, d_theta, d_w_eff=None, d_b_eff=None, d_geo2=None, image=None, mode="auto"):
+    """image: the operand image of field_prepare_raw for the SAME theta -- with it large launches run the tensor-core kernel.
+    mode: "auto" (library dispatch) | "simt" (exact fp32 kernel) | "tc" (tensor-core kernel or an error)."""
     f = spec.c_field(lib, table, theta, image)
-    _call(lib, "field_backward_simt" if simt else "field_backward", lib.dll.ls2fm_field_backward_simt if simt else lib.dll.ls2fm_field_backward, f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
+    if mode == "tc" and (image is None or (g_nrm is None and g_rgb is None)):
+        mode = "auto"       # no operand image / no gradient on the normals: nothing for the tensor-core kernel to do
+    name = {"auto": "field_backward", "simt": "field_backward_simt", "tc": "field_backward_tc"}[mode]
+    _call(lib, name, getattr(lib.dll, "ls2fm_" + name), f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
         lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), lib.stream())
 
 
@@ -293,7 +297,7 @@ def composite_backward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, 
 
 
 # ------------------------------------------------------------------------- autograd
-BACKWARD_SIMT = False      # tests flip this to cross-check the tensor-core backward kernel against the fp32-SIMT one
+BACKWARD_MODE = "auto"     # tests set "simt" / "tc" to cross-check the tensor-core backward kernel against the fp32-SIMT one
 
 def _c(t):
     return None if t is None else t.contiguous()
@@ -353,7 +357,7 @@ class FieldEval(torch.autograd.Function):
         d_b = torch.zeros_like(b_eff) if with_rad else None
         d_geo2 = torch.empty_like(geo2) if (with_rad and geo2 is not None) else None
         field_backward_raw(lib, spec, table, theta, pts, rad, g_y, g_sdf, g_nrm, g_rgb, s_nrm, s_rgb,
-                           d_table, d_theta, d_w, d_b, d_geo2, image=ctx.image, simt=BACKWARD_SIMT)
+                           d_table, d_theta, d_w, d_b, d_geo2, image=ctx.image, mode=BACKWARD_MODE)
         return (None, None, d_table, d_theta, d_w, d_b, d_geo2, None, None, None, None, None, None, None, None, None)
 
 

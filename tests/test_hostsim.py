@@ -45,9 +45,15 @@ def test_hash_indices_bit_exact(hostsim_lib):
     ("bmvs", 16, (None, 64, 16), 12, 4, True),
     ("DTU", 16, (None, 64, 64, 16), 33, 3, False),
 ])
-def test_render_forward_backward_matches_oracle(dataset, n_levels, layers, n_samples, n_rays, dual):
+@pytest.mark.parametrize("mode", ["auto", "tc"])     # auto: these sizes run the exact SIMT backward; tc: force the tensor-core kernel
+def test_render_forward_backward_matches_oracle(dataset, n_levels, layers, n_samples, n_rays, dual, mode):
+    from levels2fm_b200 import ops
     opt = common.make_opt(dataset, "cpu", n_levels, layers, n_samples, dual)
-    outs, grads = common.render_parity_case(opt, n_levels, 2, n_rays)
+    ops.BACKWARD_MODE = mode
+    try:
+        outs, grads = common.render_parity_case(opt, n_levels, 2, n_rays)
+    finally:
+        ops.BACKWARD_MODE = "auto"
     for k, (a, b) in outs.items():
         assert common.rel_err(a, b) < 1e-4, k
     for k, (a, b) in grads.items():
@@ -60,15 +66,17 @@ def test_tensor_core_backward_agrees_with_simt_backward():
     from levels2fm_b200 import ops
     res = {}
     for simt in (True, False):
-        ops.BACKWARD_SIMT = simt
+        ops.BACKWARD_MODE = "simt" if simt else "tc"
         try:
             opt = common.make_opt("DTU", "cpu", 16, (None, 64, 64, 16), 21, False)
             _, res[simt] = common.render_parity_case(opt, 16, 2, 5)
         finally:
-            ops.BACKWARD_SIMT = False
+            ops.BACKWARD_MODE = "auto"
     for k in res[True]:
         a, b = res[False][k][0], res[True][k][0]
-        assert common.rel_err(a, b) < 5e-5, (k, common.rel_err(a, b))
+        # (the tensor-core kernel rounds the layer inputs of its weight gradients to tf32: 2^-12 per term, and this case has only
+        #  420 rows to average over -- which is why the library keeps launches this small on the exact kernel)
+        assert common.rel_err(a, b) < 1e-3, (k, common.rel_err(a, b))
 
 
 def test_golden_c1_through_kernels():
