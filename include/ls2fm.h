@@ -185,12 +185,11 @@ int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts,
                          const float* saved_nrm, const float* saved_rgb,
                          float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
                          void* stream);
-/* ls2fm_field_backward dispatches: launches of >= 32768 samples whose normals carry gradient (field.tc_image set,
- * n_levels % 4 == 0) run the tcgen05 kernel -- every matrix product of the 2-channel forward / reverse pass as 3xTF32
- * tensor-core batches (fp32-level), weights streamed from the operand image, weight gradients accumulated in TMEM with the
- * layer inputs rounded to tf32 (unbiased 2^-12 per term; averages out over the rows, which is why small launches stay on the
- * exact kernel).  _simt forces the fp32-SIMT kernel (exact; cross-check and fallback), _tc forces the tensor-core kernel and
- * fails when its preconditions do not hold. */
+/* ls2fm_field_backward dispatches: launches of >= 8192 samples whose normals carry gradient (field.tc_image set,
+ * n_levels % 4 == 0) run the tcgen05 kernel -- every matrix product of the 2-channel forward / reverse pass and every weight
+ * gradient as 3xTF32 tensor-core batches (fp32-level), weights streamed from the operand image, weight gradients accumulated in
+ * TMEM, the next tile's loads and the previous tile's scatter hidden under the batches.  _simt forces the fp32-SIMT kernel
+ * (cross-check and fallback), _tc forces the tensor-core kernel and fails when its preconditions do not hold. */
 int ls2fm_field_backward_simt(const ls2fm_field_t* field, const ls2fm_points_t* pts,
                               const ls2fm_radiance_t* rad,
                               const float* g_y, const float* g_sdf, const float* g_nrm, const float* g_rgb,

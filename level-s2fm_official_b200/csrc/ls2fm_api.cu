@@ -337,8 +337,7 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
     const int KL = field->n_layers;
     // ---- tensor-core kernel: needs the operand image (weights stream from it), the 2-channel form (normals carry gradient),
     //      chunk-aligned level groups and matrices that fit a ring slot; everything else runs the fp32-SIMT kernel below
-    //      Its weight gradients round the layer inputs to tf32 (2^-12 relative, unbiased, per term of a sum over all rows), which
-    //      only averages out over many rows: launches below LS_BT_MIN_SAMPLES stay on the exact kernel (they are latency-bound anyway).
+    //      Launches below LS_BT_MIN_SAMPLES stay on the SIMT kernel: a few tiles do not amortise the tensor-core kernel's set-up.
     const bool tc_ok = tan && field->tc_image && (field->n_levels & 3) == 0;
     if (mode == 2 && !tc_ok) return ls_fail("field_backward_tc: needs field.tc_image, a gradient on the normals and n_levels % 4 == 0");
     if ((mode == 2 || (mode == 0 && pts->n >= LS_BT_MIN_SAMPLES)) && tc_ok) {
@@ -346,7 +345,8 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
         const LsBtNet net = ls_plan_bt(*field, with_rad ? rad->in_dim : 0);
         const int smem = net.total * (int)sizeof(float);
         bool fits = smem <= ls_max_smem() && img.k_in_pad[0] <= LS_BT_EROWS && img.n_in_pad[0] <= LS_BT_EROWS;
-        for (int l = 0; l < KL - 1; ++l) fits = fits && 2 * img.n_out_pad[l] * img.k_in_pad[l] <= LS_BT_SLOT && 2 * img.n_in_pad[l] * LS_H <= LS_BT_SLOT;
+        if (with_rad) fits = fits && 3 * (rad->in_dim - rad->k_geo) + 3 <= 160;      // W_eff-gradient reducers: the last five warps
+        for (int l = 0; l < KL - 1; ++l) fits = fits && img.n_out_pad[l] * img.k_in_pad[l] <= LS_BT_SLOT && img.n_in_pad[l] * LS_H <= LS_BT_SLOT;
         if (fits) {
             a.net = ls_plan_net(*field, with_rad ? rad->in_dim : 0, 1, false);        // theta offsets
             const int64_t n_tiles = (pts->n + LS_BT_TILE - 1) / LS_BT_TILE;

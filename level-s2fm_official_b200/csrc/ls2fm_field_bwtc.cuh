@@ -32,14 +32,15 @@
 
 constexpr int LS_BT_THREADS = 512;
 constexpr int LS_BT_TILE = 64;                  // samples per tile
-constexpr int64_t LS_BT_MIN_SAMPLES = 32768;    // automatic dispatch: smaller launches run the exact fp32-SIMT kernel
+constexpr int64_t LS_BT_MIN_SAMPLES = 8192;     // automatic dispatch: smaller launches run the fp32-SIMT kernel
 constexpr int LS_BT_KG = 32;                    // groups of 4 rows in a staging array (128 rows)
 constexpr int LS_BT_LBO = LS_H * 16 + 16;       // bytes between row groups of a 64-feature staging array (+16: conflict-free stores)
 constexpr int LS_BT_LBOF = LS_BT_LBO / 4;       // ... in floats (260)
 constexpr int LS_BT_EROWS = 48;                 // feature rows of the encoding stash (35 + ones -> 40, MMA N = 48)
 constexpr int LS_BT_LBO_E = LS_BT_EROWS * 16 + 16;
 constexpr int LS_BT_LBOF_E = LS_BT_LBO_E / 4;   // 196
-constexpr int LS_BT_SLOT = 8192;                // floats per ring slot (32 KB: a 64 x 64 hi/lo pair)
+constexpr int LS_BT_SLOT = 4096;                // floats per ring slot (16 KB: the hi OR the lo half of a 64 x 64 operand)
+constexpr int LS_BT_PBP = 17;                   // pitch of a per-sample staging row (odd: conflict-free across the 16 samples of a warp)
 // TMEM columns
 constexpr int LS_BT_WG = 0;                     // weight-gradient accumulators: last^T [0,32) | layer 0 [24,72) | layer l [64 l, +64)
 constexpr int LS_BT_A = 192;                    // A_k at LS_BT_A + 64 (k - 1)
@@ -47,9 +48,10 @@ constexpr int LS_BT_LO = 384;
 constexpr int LS_BT_D = 448;
 
 struct LsBtNet {         // shared-memory plan (float offsets)
-    int zr, zl, ar;      // staging: adjoint raw / lo, layer input (tf32-rounded)    [32 groups][64 features][4 rows] padded
+    int zr, zl, ar, al;  // staging: adjoint raw / lo, layer input raw / lo           [32 groups][64 features][4 rows] padded
     int es;              // encoding stash (raw), operand of the layer-0 weight gradient [32 groups][48 features][4 rows] padded
-    int ring;            // 2 slots
+    int pbn;             // per-sample upstream values, 3 tiles deep (previous: deferred scatter, current, next: prefetch) [3][64][16]
+    int ring;            // 3 slots
     int bias[LS2FM_MAX_LAYERS];
     int weff, rad_pitch;
     int gs;              // [3][64] scratch of the final flush
@@ -65,8 +67,10 @@ inline LsBtNet ls_plan_bt(const ls2fm_field_t& f, int rad_in_dim) {
     n.zr = off; off += stage;
     n.zl = off; off += stage;
     n.ar = off; off += stage;
+    n.al = off; off += stage;
     n.es = off; off += LS_BT_KG * LS_BT_LBOF_E;
-    n.ring = off; off += 2 * LS_BT_SLOT;         // also absorbs the M = 128 over-read of the arrays above
+    n.pbn = ls_round4(off); off = n.pbn + 3 * LS_BT_TILE * LS_BT_PBP;
+    n.ring = off; off += 3 * LS_BT_SLOT;
     for (int l = 0; l < f.n_layers; ++l) { n.bias[l] = off; off += LS_H; }
     n.rad_pitch = ls_round4(rad_in_dim > 0 ? rad_in_dim : 4);
     n.weff = off; off += 3 * n.rad_pitch + 4;
@@ -83,36 +87,32 @@ LS_DEV void ls_bt_matrix(const LsTcNet& img, int H, int b, int* src, int* floats
     else { const int l = 2 * H - b; *src = img.wt_hi[l]; *floats = 2 * img.n_in_pad[l] * LS_H; }
 }
 
-// weight-gradient batch: D[m][d_col + n] += sum_r A(m, r) B(n, r) over the tile's 128 rows.  One operand ("split": the adjoint) is
-// exact as raw + lo (raw read as tf32 by truncation); the other ("single": the layer input) was rounded to tf32 (rna) when it was
-// staged -- an unbiased 2^-12 relative perturbation of each term of a sum over >= thousands of rows, far below the fp32 atomics'
-// own reordering noise.  split_is_a: the split operand is A (M = its features), else B.
-LS_DEV void ls_bt_wgrad(uint32_t tmem, int d_col, const float* p_raw, const float* p_lo, int p_lbo, const float* s_hi, int s_lbo, int N,
-                        bool split_is_a) {
+// weight-gradient batch: D[m][d_col + n] += sum_r A(m, r) B(n, r) over the tile's 128 rows, 3xTF32 (raw = hi by truncation).
+// (Rounding one operand to tf32 instead of carrying its lo part was tried: the 2^-12 noise per term does not average out against
+//  the gradient -- a sum of large cancelling terms -- and showed up as 3e-3 of the output layer's weight_g gradient on 16 k samples.)
+LS_DEV void ls_bt_wgrad(uint32_t tmem, int d_col, const float* a_raw, const float* a_lo, int a_lbo, const float* b_raw, const float* b_lo,
+                        int b_lbo, int N) {
 #if defined(LS_HOSTSIM)
     for (int ks = 0; ks < LS_BT_KG / 2; ++ks) {      // 8 rows (two groups of 4) per MMA
-        const int po = ks * 2 * (p_lbo / 4), so = ks * 2 * (s_lbo / 4);
-        if (split_is_a) {
-            ls_tc_mma_ss(tmem, d_col, p_lo + po, p_lbo, s_hi + so, s_lbo, N, true);
-            ls_tc_mma_ss(tmem, d_col, p_raw + po, p_lbo, s_hi + so, s_lbo, N, true);
-        } else {
-            ls_tc_mma_ss(tmem, d_col, s_hi + so, s_lbo, p_lo + po, p_lbo, N, true);
-            ls_tc_mma_ss(tmem, d_col, s_hi + so, s_lbo, p_raw + po, p_lbo, N, true);
-        }
+        const int ao = ks * 2 * (a_lbo / 4), bo = ks * 2 * (b_lbo / 4);
+        ls_tc_mma_ss(tmem, d_col, a_lo + ao, a_lbo, b_raw + bo, b_lbo, N, true);
+        ls_tc_mma_ss(tmem, d_col, a_raw + ao, a_lbo, b_lo + bo, b_lbo, N, true);
+        ls_tc_mma_ss(tmem, d_col, a_raw + ao, a_lbo, b_raw + bo, b_lbo, N, true);
     }
 #else
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(LS_TC_M >> 4) << 24);
-    uint64_t pr = ls_tc_desc(ls_smem_u32(p_raw), (uint32_t)p_lbo, 128), pl = ls_tc_desc(ls_smem_u32(p_lo), (uint32_t)p_lbo, 128);
-    uint64_t sh = ls_tc_desc(ls_smem_u32(s_hi), (uint32_t)s_lbo, 128);
-    const uint64_t ps = (uint64_t)(2 * p_lbo >> 4), ss = (uint64_t)(2 * s_lbo >> 4);     // 8 rows (two groups of 4) per MMA
+    uint64_t ar = ls_tc_desc(ls_smem_u32(a_raw), (uint32_t)a_lbo, 128), al = ls_tc_desc(ls_smem_u32(a_lo), (uint32_t)a_lbo, 128);
+    uint64_t br = ls_tc_desc(ls_smem_u32(b_raw), (uint32_t)b_lbo, 128), bl = ls_tc_desc(ls_smem_u32(b_lo), (uint32_t)b_lbo, 128);
+    const uint64_t as = (uint64_t)(2 * a_lbo >> 4), bs = (uint64_t)(2 * b_lbo >> 4);     // 8 rows (two groups of 4) per MMA
     const uint32_t d = tmem + (uint32_t)d_col;
 #define LS_BT_SS(A, B) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" \
                                     :: "r"(d), "l"(A), "l"(B), "r"(idesc))
 #pragma unroll
     for (int ks = 0; ks < LS_BT_KG / 2; ++ks) {
-        if (split_is_a) { LS_BT_SS(pl, sh); LS_BT_SS(pr, sh); }
-        else { LS_BT_SS(sh, pl); LS_BT_SS(sh, pr); }
-        pr += ps; pl += ps; sh += ss;
+        LS_BT_SS(al, br);
+        LS_BT_SS(ar, bl);
+        LS_BT_SS(ar, br);
+        ar += as; al += as; br += bs; bl += bs;
     }
 #undef LS_BT_SS
 #endif
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     const int RP = net.rad_pitch;
     const int nin = rad ? a.r.in_dim - kg : 0;      // radiance inputs that are not geo features: x, n, dir, Fourier, (geo2)
     const float* Weff = smem + net.weff;
-    float* ZR = smem + net.zr; float* ZL = smem + net.zl; float* AR = smem + net.ar;
+    float* ZR = smem + net.zr; float* ZL = smem + net.zl; float* AR = smem + net.ar; float* AL = smem + net.al;
     float* ES = smem + net.es;
     float* RIN = ZR;                                // [64][nin] radiance inputs of the tile (dead before the staging arrays are written)
     float* PB = ZL;                                 // [64][4]  radiance pre-activation gradients
@@ -154,13 +154,11 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     }
     for (int e = t; e < LS_BT_KG * LS_BT_LBOF_E; e += LS_BT_THREADS) ES[e] = 0.f;     // feature rows >= k_in_pad stay zero for ever
     LsTcBar* bar = reinterpret_cast<LsTcBar*>(smem + net.misc);
-    LsTcBar* full0 = reinterpret_cast<LsTcBar*>(smem + net.misc + 2);
-    LsTcBar* full1 = reinterpret_cast<LsTcBar*>(smem + net.misc + 4);
-    LsTcBar* bar2 = reinterpret_cast<LsTcBar*>(smem + net.misc + 6);     // weight-gradient batches (off the critical path)
-    const uint32_t tmem = ls_tc_alloc(reinterpret_cast<uint32_t*>(smem + net.misc + 8));
+    LsTcBar* bar2 = reinterpret_cast<LsTcBar*>(smem + net.misc + 8);     // weight-gradient batches (off the critical path)
+    const uint32_t tmem = ls_tc_alloc(reinterpret_cast<uint32_t*>(smem + net.misc + 10));
     ls_tc_bar_init(bar);
     ls_tc_bar_init(bar2);
-    if (t == 0) { ls_bar_init1(full0); ls_bar_init1(full1); }
+    if (t == 0) { for (int s3 = 0; s3 < 3; ++s3) ls_bar_init1(reinterpret_cast<LsTcBar*>(smem + net.misc + 2 + 2 * s3)); }
     ls_fence_smem_to_async();
     __syncthreads();
     uint32_t phase = 0, phase2 = 0;
@@ -174,24 +172,38 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     const int64_t n_tiles = (a.p.n + LS_BT_TILE - 1) / LS_BT_TILE;
     const int64_t my_tiles = n_tiles > (int64_t)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t n_batches = my_tiles * NB;
-    int64_t gb = 0;                     // running batch index (ring position)
-    auto ring_fetch = [&](int64_t g) {  // thread 0: start the copy of batch g's matrix into slot g & 1
-        if (g < n_batches) {
+    int64_t gb = 0;                     // running batch index
+    // ring entries: 2 per batch (the hi half of its matrix, then the lo half), entry e lives in slot e % 3 and completes full[e % 3]
+    // for the (e / 3)-th time.  Entries 0..2 are fetched up front; when batch g is done its two slots are refilled with entries
+    // 2g+3 (the lo half of batch g+1's matrix) and 2g+4 (the hi half of batch g+2's).
+    auto ring_fetch = [&](int64_t e) {  // one thread
+        if (e < 2 * n_batches) {
             int src, floats;
-            ls_bt_matrix(img, H, (int)(g % NB), &src, &floats);
-            ls_bulk_g2s(smem + net.ring + (int)(g & 1) * LS_BT_SLOT, a.f.tc_image + src, floats * 4, (g & 1) ? full1 : full0);
+            ls_bt_matrix(img, H, (int)((e >> 1) % NB), &src, &floats);
+            const int half = floats / 2, s3 = (int)(e % 3);
+            ls_bulk_g2s(smem + net.ring + s3 * LS_BT_SLOT, a.f.tc_image + src + (int)(e & 1) * half, half * 4,
+                        reinterpret_cast<LsTcBar*>(smem + net.misc + 2 + 2 * s3));
         }
     };
-    if (t == 0) { ring_fetch(0); ring_fetch(1); }
-    // warp 0, after the barrier of batch g: wait for its matrix; returns the slot
-    auto ring_slot = [&](int64_t g) -> const float* {
-        ls_bar_wait((g & 1) ? full1 : full0, (uint32_t)((g >> 1) & 1));
-        return smem + net.ring + (int)(g & 1) * LS_BT_SLOT;
+    if (t == 0) { ring_fetch(0); ring_fetch(1); ring_fetch(2); }
+    // the issuing lane: wait for entry e; returns its slot
+    auto ring_slot = [&](int64_t e) -> const float* {
+        const int s3 = (int)(e % 3);
+        ls_bar_wait(reinterpret_cast<LsTcBar*>(smem + net.misc + 2 + 2 * s3), (uint32_t)((e / 3) & 1));
+        return smem + net.ring + s3 * LS_BT_SLOT;
     };
-    // all threads: wait for batch g, then thread 0 refills its slot with the matrix of batch g + 2
+    // 3xTF32 product of batch gb by the issuing lane: D = A_lo W_hi + A_raw W_hi, then (second ring entry) + A_raw W_lo
+    auto issue_x3 = [&](int d_col, int a_raw_col, int a_lo_col, int N, int Kd) {
+        const float* Wh = ring_slot(2 * gb);
+        ls_tc_mma(tmem, d_col, a_lo_col, Wh, N, Kd, false);
+        ls_tc_mma(tmem, d_col, a_raw_col, Wh, N, Kd, true);
+        const float* Wl = ring_slot(2 * gb + 1);
+        ls_tc_mma(tmem, d_col, a_raw_col, Wl, N, Kd, true);
+    };
+    // all threads: wait for batch gb, then one lane refills its two slots
     auto batch_done = [&]() {
         ls_tc_wait(bar, phase);
-        if (warp == 0) { if (ls_elect()) ring_fetch(gb + 2); }
+        if (warp == 0) { if (ls_elect()) { ring_fetch(2 * gb + 3); ring_fetch(2 * gb + 4); } }
         ++gb;
     };
     // persistent accumulators
@@ -206,50 +218,195 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     const int st_off_e = (row >> 2) * LS_BT_LBOF_E + (row & 3);
     const int colE = LS_BT_A + 64 * (H - 1);
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ------------------------------------------------ B1: upstream gradients of this thread's sample
-        if (wg_pending) { ls_tc_wait(bar2, phase2); wg_pending = false; }    // the stash / staging arrays are rewritten below
-        const int64_t i_in = tile * LS_BT_TILE + sl;
-        const bool valid = i_in < a.p.n;
-        float x[3] = {0.f, 0.f, 0.f}, u[3];
-        int ray_id = 0;
-        int64_t i = i_in;
-        if (valid) ls_sample_point(a.p, i_in, x, &ray_id, &i);
-        ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
-        float pbar[3] = {0.f, 0.f, 0.f}, nbar[3] = {0.f, 0.f, 0.f};
-        if (valid) {
-            if (rad && a.g_rgb) {
+    // ------------------------------------------------ software pipeline across tiles
+    // The memory work of a tile is issued under the tensor-core batches of its neighbours, by the same warps:
+    //   under B5 of tile n  : the per-sample loads of tile n+1 (position, upstream gradients, saved outputs) -> PBN[next]
+    //   under B6 of tile n  : the hash-grid gather of tile n+1 (this thread's two levels) -> 8 registers
+    //   under B4 of tile n+1: the hash-table gradient scatter of tile n (adjoints kept in 8 registers, cell from PBN[previous])
+    // PBN row: 0..2 pbar | 3..5 upstream normal gradient | 6..8 position | 9..11 ray direction | 12..14 saved normal | 15 valid
+    float* PBN = smem + net.pbn;
+    int pb_prev = 2, pb_cur = 0, pb_nxt = 1;
+    auto stage_sample = [&](int64_t tile, int buf) {        // raw per-sample loads, spread over the sample's 8 threads
+        float* P = PBN + (buf * LS_BT_TILE + sl) * LS_BT_PBP;
+        const int64_t i = tile * LS_BT_TILE + sl;           // (dense launches: output index == input index)
+        const bool valid = tile < n_tiles && i < a.p.n;
+        float v3[3] = {0.f, 0.f, 0.f};
+        int base = -1;
+        if (!isT) {
+            if (cg == 0) {
+                if (valid) { int ray_id; int64_t io; ls_sample_point(a.p, i, v3, &ray_id, &io); }
+                base = 6;
+                P[15] = valid ? 1.f : 0.f;
+            } else if (cg == 1) {
+                if (valid && rad && a.g_rgb) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float rgb = __ldg(a.saved_rgb + 3 * i + c);
-                    pbar[c] = __ldg(a.g_rgb + 3 * i + c) * rgb * (1.f - rgb);
+                    for (int c = 0; c < 3; ++c) {
+                        const float rgb = __ldg(a.saved_rgb + 3 * i + c);
+                        v3[c] = __ldg(a.g_rgb + 3 * i + c) * rgb * (1.f - rgb);
+                    }
                 }
-            }
+                base = 0;
+            } else if (cg == 2) {
+                if (valid && a.g_nrm) {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                float v = a.g_nrm ? __ldg(a.g_nrm + 3 * i + d) : 0.f;
-                if (rad) v += Weff[3 + d] * pbar[0] + Weff[RP + 3 + d] * pbar[1] + Weff[2 * RP + 3 + d] * pbar[2];
-                nbar[d] = v;
+                    for (int d = 0; d < 3; ++d) v3[d] = __ldg(a.g_nrm + 3 * i + d);
+                }
+                base = 3;
+            } else {
+                if (valid && rad) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) v3[d] = __ldg(a.saved_nrm + 3 * i + d);
+                }
+                base = 12;
+            }
+        } else if (cg == 0) {
+            if (valid && rad) {
+                const int64_t r = i / a.p.n_per_ray;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) v3[d] = __ldg(a.p.ray + 3 * r + d);
+            }
+            base = 9;
+        }
+        if (base >= 0) { P[base] = v3[0]; P[base + 1] = v3[1]; P[base + 2] = v3[2]; }
+    };
+    // nbar = upstream normal gradient + W_eff[:, 3:6]^T pbar
+    auto load_nbar = [&](const float* P, float (&nbar)[3]) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float v = P[3 + d];
+            if (rad) v += Weff[3 + d] * P[0] + Weff[RP + 3 + d] * P[1] + Weff[2 * RP + 3 + d] * P[2];
+            nbar[d] = v;
+        }
+    };
+    float e4[4], d4[4];                 // gather in flight (next tile)
+    float pl[2][3];                     // ... its z = 0 plane of the level being evaluated: value, d/dx, d/dy per feature
+    // The gather of a tile is cut into four pieces, one per tensor-core batch it hides under: piece p = (level r = p >> 1 of this
+    // thread's two levels 4 cg + 2 isT + r, z-plane p & 1 of the cell: 4 of the 8 corner loads).  Same arithmetic, term by term,
+    // as ls_level_eval.  Piece 2r+1 completes level r: features e and tangent features Je nbar.
+    auto gather_piece = [&](int buf, int p) {
+        const int r = p >> 1, plane = p & 1;
+        const float* P = PBN + (buf * LS_BT_TILE + sl) * LS_BT_PBP;
+        const float x[3] = {P[6], P[7], P[8]};
+        float u[3];
+        ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
+        const int l = 4 * cg + 2 * isT + r;
+        const float scale = a.f.levels[l].scale;
+        const uint32_t res = a.f.levels[l].resolution, size = a.f.levels[l].size, hashed = a.f.levels[l].hashed;
+        const float2* tab = reinterpret_cast<const float2*>(a.f.table) + a.f.levels[l].offset;
+        const LsCell c = ls_cell(scale, u);
+        float2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(tab + ls_corner_index(res, size, hashed, c, 4 * plane + k));
+        const float w0 = c.w[0], w1 = c.w[1], w2 = c.w[2];
+        const float m0 = 1.f - w0, m1 = 1.f - w1, m2 = 1.f - w2;
+        float nbar[3];
+        if (plane) load_nbar(P, nbar);
+#pragma unroll
+        for (int fi = 0; fi < 2; ++fi) {
+            const float q0 = fi ? v[0].y : v[0].x, q1 = fi ? v[1].y : v[1].x, q2 = fi ? v[2].y : v[2].x, q3 = fi ? v[3].y : v[3].x;
+            const float a0 = m0 * q0 + w0 * q1, a1 = m0 * q2 + w0 * q3;
+            const float b = m1 * a0 + w1 * a1, gx = m1 * (q1 - q0) + w1 * (q3 - q2), gy = a1 - a0;
+            if (!plane) { pl[fi][0] = b; pl[fi][1] = gx; pl[fi][2] = gy; }
+            else {
+                const float dh0 = scale * (m2 * pl[fi][1] + w2 * gx), dh1 = scale * (m2 * pl[fi][2] + w2 * gy), dh2 = scale * (b - pl[fi][0]);
+                e4[2 * r + fi] = m2 * pl[fi][0] + w2 * b;
+                d4[2 * r + fi] = dh0 * a.inv_ext[0] * nbar[0] + dh1 * a.inv_ext[1] * nbar[1] + dh2 * a.inv_ext[2] * nbar[2];
             }
         }
-        if (rad) {
-            // radiance inputs of the W_eff gradient, spread over the 8 threads of the sample
-            float* in = RIN + sl * nin;
-            float dir[3] = {0.f, 0.f, 0.f};
-            if (valid) {
+    };
+    float c8n[8];                       // gathered chunk of the next tile: primal row e / tangent row edot, columns 8 cg .. 8 cg + 7
+    auto gather_finish = [&]() {        // the two rows of a sample swap halves
 #pragma unroll
-                for (int d = 0; d < 3; ++d) dir[d] = __ldg(a.p.ray + 3 * ray_id + d);
+        for (int k = 0; k < 4; ++k) {
+            const float r = __shfl_xor_sync(0xffffffffu, isT ? e4[k] : d4[k], 16);
+            c8n[k] = isT ? r : e4[k];           // primal row: features of levels 4cg, 4cg+1 (own), 4cg+2, 4cg+3 (partner)
+            c8n[4 + k] = isT ? d4[k] : r;       // tangent row: edot likewise
+        }
+    };
+    float sb[4], sd[4];                 // deferred scatter (previous tile): adjoints of my two levels' features / tangent features
+    bool sc_pending = false;
+    auto scatter_level = [&](int buf, int r, float e0, float e1, float t0, float t1) {
+        const float* P = PBN + (buf * LS_BT_TILE + sl) * LS_BT_PBP;
+        if (!a.d_table || P[15] == 0.f) return;
+        const float x[3] = {P[6], P[7], P[8]};
+        float u[3], nbar[3];
+        load_nbar(P, nbar);
+        ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
+        const int l = 4 * cg + 2 * isT + r;
+        const float scale = a.f.levels[l].scale;
+        const uint32_t res = a.f.levels[l].resolution, size = a.f.levels[l].size, hashed = a.f.levels[l].hashed;
+        float* tab = a.d_table + 2 * (size_t)a.f.levels[l].offset;
+        const LsCell c = ls_cell(scale, u);
+        float ns[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ns[d] = nbar[d] * scale * a.inv_ext[d];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float f0 = (k & 1) ? c.w[0] : 1.f - c.w[0];
+            const float f1 = (k & 2) ? c.w[1] : 1.f - c.w[1];
+            const float f2 = (k & 4) ? c.w[2] : 1.f - c.w[2];
+            const float wgt = f0 * f1 * f2;
+            const float dw = ((k & 1) ? ns[0] : -ns[0]) * f1 * f2 + ((k & 2) ? ns[1] : -ns[1]) * f0 * f2 +
+                             ((k & 4) ? ns[2] : -ns[2]) * f0 * f1;
+            const uint32_t idx = ls_corner_index(res, size, hashed, c, k);
+            atomicAdd(reinterpret_cast<float2*>(tab) + idx, make_float2(wgt * e0 + dw * t0, wgt * e1 + dw * t1));
+        }
+    };
+    const bool has_levels = 4 * cg < L;
+    // prologue: the first tile's loads and gather, unhidden
+    if (my_tiles > 0) {
+        stage_sample(blockIdx.x, pb_cur);
+        __syncthreads();
+        if (has_levels) {
+            gather_piece(pb_cur, 0); gather_piece(pb_cur, 1); gather_piece(pb_cur, 2); gather_piece(pb_cur, 3);
+            gather_finish();
+        }
+    }
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const bool has_next = tile + gridDim.x < n_tiles;
+        // ------------------------------------------------ B1: this tile's encoding (gathered under the previous tile) -> TMEM + stash
+        if (wg_pending) { ls_tc_wait(bar2, phase2); wg_pending = false; }    // the stash / staging arrays are rewritten below
+        const float* Pc = PBN + (pb_cur * LS_BT_TILE + sl) * LS_BT_PBP;
+        const int64_t i = tile * LS_BT_TILE + sl;
+        const bool valid = Pc[15] != 0.f;
+        if (has_levels) {
+            float lo8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                lo8[k] = ls_tf32_lo(c8n[k]);
+                ES[st_off_e + (8 * cg + k) * 4] = c8n[k];
             }
+            ls_tmem_st(tmem, colE + 8 * cg, c8n, 8);
+            ls_tmem_st(tmem, LS_BT_LO + 8 * cg, lo8, 8);
+        }
+        if (cg == 0) {      // tail chunk: x / rescale (tangent row: nbar / rescale), the ones column (primal rows only), zero padding
+            float nbar[3];
+            load_nbar(Pc, nbar);
+            float c8[8] = {0.f, 0.f, 0.f, isT ? 0.f : 1.f, 0.f, 0.f, 0.f, 0.f}, lo8[8];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) c8[d] = isT ? nbar[d] / a.f.rescale : ls_fdiv(Pc[6 + d], a.f.rescale);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                lo8[k] = ls_tf32_lo(c8[k]);
+                ES[st_off_e + (nh + k) * 4] = c8[k];
+            }
+            ls_tmem_st(tmem, colE + nh, c8, 8);
+            ls_tmem_st(tmem, LS_BT_LO + nh, lo8, 8);
+        }
+        // ------------------------------------------------ B2/B3: W_eff gradient, non-geo inputs (x, n, dir, Fourier, geo2) and b_eff
+        if (rad) {
+            float* in = RIN + sl * nin;
             if (!isT) {
                 if (cg == 0) {
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) { in[d] = x[d]; PB[4 * sl + d] = pbar[d]; }
+                    for (int d = 0; d < 3; ++d) { in[d] = Pc[6 + d]; PB[4 * sl + d] = Pc[d]; }
                 } else if (cg == 1) {
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) in[3 + d] = valid ? __ldg(a.saved_nrm + 3 * i + d) : 0.f;
+                    for (int d = 0; d < 3; ++d) in[3 + d] = Pc[12 + d];
                 } else if (cg == 2) {
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) in[6 + d] = dir[d];
+                    for (int d = 0; d < 3; ++d) in[6 + d] = Pc[9 + d];
                 } else {
                     for (int k = 0; k < kg2; ++k) in[o_geo + k] = valid ? __ldg(a.r.geo2 + i * (kg2 + 1) + 1 + k) : 0.f;
                 }
@@ -258,7 +415,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                         float v = 0.f;
                         if (k >= 1) {
                             const int col = o_geo2 + k - 1;
-                            v = Weff[col] * pbar[0] + Weff[RP + col] * pbar[1] + Weff[2 * RP + col] * pbar[2];
+                            v = Weff[col] * Pc[0] + Weff[RP + col] * Pc[1] + Weff[2 * RP + col] * Pc[2];
                         }
                         a.d_geo2[i * (kg2 + 1) + k] = v;
                     }
@@ -268,66 +425,13 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                     const float fr = (float)(1 << k);
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        const float ang = dir[d] * fr;
+                        const float ang = Pc[9 + d] * fr;
                         in[9 + 6 * k + d] = sinf(ang);
                         in[12 + 6 * k + d] = cosf(ang);
                     }
                 }
             }
-        }
-        // ------------------------------------------------ B2: gather.  This thread: levels 4 cg + 2 isT + {0, 1}; features e and
-        //                                                   tangent features edot = Je nbar; the two rows of the sample swap halves
-        if (4 * cg < L) {
-            float e4[4], d4[4];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int l = 4 * cg + 2 * isT + r;
-                float h[2], dh[2][3];
-                ls_level_eval(a.f, l, u, h, dh);
-#pragma unroll
-                for (int fi = 0; fi < 2; ++fi) {
-                    e4[2 * r + fi] = h[fi];
-                    d4[2 * r + fi] = dh[fi][0] * a.inv_ext[0] * nbar[0] + dh[fi][1] * a.inv_ext[1] * nbar[1] + dh[fi][2] * a.inv_ext[2] * nbar[2];
-                }
-            }
-            float c8[8], lo8[8];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float r = __shfl_xor_sync(0xffffffffu, isT ? e4[k] : d4[k], 16);
-                c8[k] = isT ? r : e4[k];            // primal row: features of levels 4cg, 4cg+1 (own), 4cg+2, 4cg+3 (partner)
-                c8[4 + k] = isT ? d4[k] : r;        // tangent row: edot likewise
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                lo8[k] = ls_tf32_lo(c8[k]);
-                ES[st_off_e + (8 * cg + k) * 4] = ls_tf32_rna(c8[k]);
-            }
-            ls_tmem_st(tmem, colE + 8 * cg, c8, 8);
-            ls_tmem_st(tmem, LS_BT_LO + 8 * cg, lo8, 8);
-        }
-        if (cg == 0) {      // tail chunk: x / rescale (tangent row: nbar / rescale), the ones column (primal rows only), zero padding
-            float c8[8] = {0.f, 0.f, 0.f, isT ? 0.f : 1.f, 0.f, 0.f, 0.f, 0.f}, lo8[8];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) c8[d] = isT ? nbar[d] / a.f.rescale : ls_fdiv(x[d], a.f.rescale);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                lo8[k] = ls_tf32_lo(c8[k]);
-                ES[st_off_e + (nh + k) * 4] = ls_tf32_rna(c8[k]);
-            }
-            ls_tmem_st(tmem, colE + nh, c8, 8);
-            ls_tmem_st(tmem, LS_BT_LO + nh, lo8, 8);
-        }
-        // ------------------------------------------------ B3: W_eff gradient, non-geo inputs (x, n, dir, Fourier, geo2) and b_eff
-        if (rad) {
-            __syncthreads();
-            if (t < 3 * nin + 3) {
-                const int c = t < 3 * nin ? t / nin : t - 3 * nin;
-                const int idx = t < 3 * nin ? t - c * nin : -1;
-                float acc = 0.f;
-#pragma unroll 4
-                for (int s = 0; s < LS_BT_TILE; ++s) acc = fmaf(PB[4 * s + c], idx >= 0 ? RIN[s * nin + idx] : 1.f, acc);
-                weff_acc += acc;
-            }
+            // (reduced under the forward batches below, after the barrier in front of the first one)
         }
         // ------------------------------------------------ B4: forward, both channels per batch
 #pragma unroll
@@ -335,12 +439,25 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
             const int a_col = l == 0 ? colE : LS_BT_A + 64 * (l - 1);
             ls_tc_sync_before_mma();
             if (warp == 0) {
-                const float* W = ring_slot(gb);
-                const int Kp = img.k_in_pad[l];
                 if (ls_elect()) {
-                    ls_tc_mma_x3(tmem, LS_BT_D, a_col, LS_BT_LO, W, W + LS_H * Kp, LS_H, Kp);
+                    issue_x3(LS_BT_D, a_col, LS_BT_LO, LS_H, img.k_in_pad[l]);
                     ls_tc_commit(bar);
                 }
+            }
+            if (rad && l == 0 && t >= LS_BT_THREADS - 160 && t - (LS_BT_THREADS - 160) < 3 * nin + 3) {
+                // W_eff / b_eff gradient of this tile (RIN / PB were completed before this batch's barrier), by the last five warps
+                const int tt = t - (LS_BT_THREADS - 160);
+                const int c = tt < 3 * nin ? tt / nin : tt - 3 * nin;
+                const int idx = tt < 3 * nin ? tt - c * nin : -1;
+                float acc = 0.f;
+#pragma unroll 4
+                for (int s = 0; s < LS_BT_TILE; ++s) acc = fmaf(PB[4 * s + c], idx >= 0 ? RIN[s * nin + idx] : 1.f, acc);
+                weff_acc += acc;
+            }
+            if (l == H - 1 && has_next) stage_sample(tile + gridDim.x, pb_nxt);     // next tile's per-sample loads run under this batch
+            if (sc_pending && has_levels) {     // the previous tile's table-gradient scatter runs under this batch
+                if (l == 0) scatter_level(pb_prev, 0, sb[0], sb[1], sd[0], sd[1]);
+                if (l == (H > 1 ? 1 : 0)) scatter_level(pb_prev, 1, sb[2], sb[3], sd[2], sd[3]);
             }
             batch_done();
             // epilogue: the primal lane takes columns 0..7 of the pair's 16, the tangent lane 8..15 (both channels of those)
@@ -382,6 +499,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                 ls_tmem_st(tmem, LS_BT_LO + 16 * cg, lo, 16);
             }
         }
+        if (H == 1 && rad) __syncthreads();     // (deeper nets: the barrier of forward batch 1 already separates the RIN readers from B5)
         // ------------------------------------------------ B5: reverse, output layer.  Row operand: primal [ybar (dout) | pbar (3) | 0],
         //                                                   tangent [s, 0, ...]: the adjoint of n = d(s y0)/dx is the tangent of y0
         {
@@ -397,9 +515,9 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                         if (o == 0) { if (a.g_sdf) v += a.s * __ldg(a.g_sdf + i); }
                         else if (rad && o - 1 < kg) {
                             const int col = o_geo + o - 1;
-                            v += Weff[col] * pbar[0] + Weff[RP + col] * pbar[1] + Weff[2 * RP + col] * pbar[2];
+                            v += Weff[col] * Pc[0] + Weff[RP + col] * Pc[1] + Weff[2 * RP + col] * Pc[2];
                         }
-                    } else if (rad && o < dout + 3) v = pbar[o - dout];
+                    } else if (rad && o < dout + 3) v = Pc[o - dout];
                 }
                 c8[k] = v;
                 lo8[k] = ls_tf32_lo(v);
@@ -413,23 +531,28 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
             ls_tmem_ld(tmem, LS_BT_A + 64 * (H - 1) + 16 * cg, ah, 16);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                AR[st_off + (16 * cg + k) * 4] = ls_tf32_rna(ah[k]);
+                AR[st_off + (16 * cg + k) * 4] = ah[k];
+                AL[st_off + (16 * cg + k) * 4] = ls_tf32_lo(ah[k]);
             }
             ls_fence_smem_to_async();
             ls_tc_sync_before_mma();
             if (warp == 0) {
-                const float* W = ring_slot(gb);
                 if (ls_elect()) {
                     // critical path first: the product into the layer below ...
-                    ls_tc_mma_x3(tmem, LS_BT_D, LS_BT_LO, LS_BT_LO + 32, W, W + LS_H * img.kl_pad, LS_H, img.kl_pad);
+                    issue_x3(LS_BT_D, LS_BT_LO, LS_BT_LO + 32, LS_H, img.kl_pad);
                     ls_tc_commit(bar);
                     // ... then the output-layer weight gradient, transposed: D[i][o] += sum_r a_H[r][i] ybar'[r][o] (columns
                     // dout..dout+2: G[c][i]); it runs under the next epilogue and is only waited for before the staging arrays change
-                    ls_bt_wgrad(tmem, LS_BT_WG, ZR, ZL, LS_BT_LBO, AR, LS_BT_LBO, 32, false);
+                    ls_bt_wgrad(tmem, LS_BT_WG, AR, AL, LS_BT_LBO, ZR, ZL, LS_BT_LBO, 32);
                     ls_tc_commit(bar2);
                 }
             }
             wg_pending = true;
+            if (has_next && has_levels) {       // next tile's gather, piece by piece under B5 and the reverse batches: slot 0 of H + 1
+#pragma unroll
+                for (int pc = 0; pc < 4; ++pc)
+                    if (pc * (H + 1) / 4 == 0) gather_piece(pb_nxt, pc);
+            }
             batch_done();
         }
         // ------------------------------------------------ B6: reverse through the hidden layers, k = H .. 1
@@ -498,69 +621,60 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
             if (k > 1) {        // input of layer k-1: a_{k-1} stack
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    AR[st_off + (16 * cg + c) * 4] = ls_tf32_rna(ap[c]);
+                    AR[st_off + (16 * cg + c) * 4] = ap[c];
+                    AL[st_off + (16 * cg + c) * 4] = ls_tf32_lo(ap[c]);
+                }
+            } else {            // input of layer 0: the stash is the raw operand, its lo part goes to AL (stash layout)
+#pragma unroll
+                for (int c = 0; c < LS_BT_EROWS / 4; ++c) {
+                    const int f = (LS_BT_EROWS / 4) * cg + c;
+                    AL[st_off_e + f * 4] = ls_tf32_lo(ES[st_off_e + f * 4]);
                 }
             }
             ls_fence_smem_to_async();
             ls_tc_sync_before_mma();
             if (warp == 0) {
-                const float* W = ring_slot(gb);
                 if (ls_elect()) {
                     if (k > 1) {
-                        ls_tc_mma_x3(tmem, LS_BT_D, colA, LS_BT_LO, W, W + LS_H * LS_H, LS_H, LS_H);
+                        issue_x3(LS_BT_D, colA, LS_BT_LO, LS_H, LS_H);
                         ls_tc_commit(bar);
-                        ls_bt_wgrad(tmem, LS_BT_WG + 64 * (k - 1), ZR, ZL, LS_BT_LBO, AR, LS_BT_LBO, LS_H, true);
+                        ls_bt_wgrad(tmem, LS_BT_WG + 64 * (k - 1), ZR, ZL, LS_BT_LBO, AR, AL, LS_BT_LBO, LS_H);
                     } else {
-                        const int N0 = img.n_in_pad[0];
-                        ls_tc_mma_x3(tmem, LS_BT_D, colA, LS_BT_LO, W, W + N0 * LS_H, N0, LS_H);
+                        issue_x3(LS_BT_D, colA, LS_BT_LO, img.n_in_pad[0], LS_H);
                         ls_tc_commit(bar);
-                        ls_bt_wgrad(tmem, LS_BT_WG + 24, ZR, ZL, LS_BT_LBO, ES, LS_BT_LBO_E, LS_BT_EROWS, true);
+                        ls_bt_wgrad(tmem, LS_BT_WG + 24, ZR, ZL, LS_BT_LBO, ES, AL, LS_BT_LBO_E, LS_BT_EROWS);
                     }
                     ls_tc_commit(bar2);
                 }
             }
+            if (has_next && has_levels) {       // slot H - k + 1 of H + 1
+#pragma unroll
+                for (int pc = 0; pc < 4; ++pc)
+                    if (pc * (H + 1) / 4 == H - k + 1) gather_piece(pb_nxt, pc);
+                if (k == 1) gather_finish();
+            }
             batch_done();
         }
-        // ------------------------------------------------ B7: hash-table gradient scatter (this thread's two levels)
-        if (4 * cg < L) {
+        // ------------------------------------------------ B7: encoding adjoints of this thread's two levels -> registers; the scatter
+        //                                                   itself runs under the next tile's forward batches
+        if (has_levels) {
             float c8[8];
             ls_tmem_ld(tmem, LS_BT_D + 8 * cg, c8, 8);
-            float eb[4], ed[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float r = __shfl_xor_sync(0xffffffffu, isT ? c8[k] : c8[4 + k], 16);
-                eb[k] = isT ? r : c8[k];            // adjoint of the features of my levels
-                ed[k] = isT ? c8[4 + k] : r;        // adjoint of their tangents
-            }
-            if (a.d_table && valid) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int l = 4 * cg + 2 * isT + r;
-                    const float scale = a.f.levels[l].scale;
-                    const uint32_t res = a.f.levels[l].resolution, size = a.f.levels[l].size, hashed = a.f.levels[l].hashed;
-                    float* tab = a.d_table + 2 * (size_t)a.f.levels[l].offset;
-                    const LsCell c = ls_cell(scale, u);
-                    const float e0 = eb[2 * r], e1 = eb[2 * r + 1], t0 = ed[2 * r], t1 = ed[2 * r + 1];
-                    float ns[3];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) ns[d] = nbar[d] * scale * a.inv_ext[d];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float f0 = (k & 1) ? c.w[0] : 1.f - c.w[0];
-                        const float f1 = (k & 2) ? c.w[1] : 1.f - c.w[1];
-                        const float f2 = (k & 4) ? c.w[2] : 1.f - c.w[2];
-                        const float wgt = f0 * f1 * f2;
-                        const float dw = ((k & 1) ? ns[0] : -ns[0]) * f1 * f2 + ((k & 2) ? ns[1] : -ns[1]) * f0 * f2 +
-                                         ((k & 4) ? ns[2] : -ns[2]) * f0 * f1;
-                        const uint32_t idx = ls_corner_index(res, size, hashed, c, k);
-                        atomicAdd(reinterpret_cast<float2*>(tab) + idx, make_float2(wgt * e0 + dw * t0, wgt * e1 + dw * t1));
-                    }
-                }
+                sb[k] = isT ? r : c8[k];            // adjoint of the features of my levels
+                sd[k] = isT ? c8[4 + k] : r;        // adjoint of their tangents
             }
         }
+        sc_pending = true;
+        { const int o = pb_prev; pb_prev = pb_cur; pb_cur = pb_nxt; pb_nxt = o; }
         // (the next tile's first tcgen05.st / staging writes are ordered after this tile's reads by ls_tmem_ld's wait::ld and by
-        //  the barrier in front of its first MMA; RIN / PB alias staging arrays whose last readers finished before batch_done)
-        if (rad) __syncthreads();
+        //  the barrier in front of its first MMA; RIN / PB alias staging arrays whose last MMA reader is waited for at the tile top)
+    }
+    if (sc_pending && has_levels) {     // the last tile's scatter
+        scatter_level(pb_prev, 0, sb[0], sb[1], sd[0], sd[1]);
+        scatter_level(pb_prev, 1, sb[2], sb[3], sd[2], sd[3]);
     }
 
     // ------------------------------------------------ flush the parameter gradients
@@ -625,11 +739,12 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     }
     if (rad && a.d_w_eff && my_tiles > 0) {
         const int in_dim = a.r.in_dim;
-        if (t < 3 * nin) {
-            const int c = t / nin, idx = t - c * nin;
+        const int tt = t - (LS_BT_THREADS - 160);
+        if (tt >= 0 && tt < 3 * nin) {
+            const int c = tt / nin, idx = tt - c * nin;
             atomicAdd(a.d_w_eff + c * in_dim + (idx < o_geo ? idx : idx + kg), weff_acc);
-        } else if (t < 3 * nin + 3) {
-            const int c = t - 3 * nin;
+        } else if (tt >= 0 && tt < 3 * nin + 3) {
+            const int c = tt - 3 * nin;
             if (a.d_b_eff) atomicAdd(a.d_b_eff + c, weff_acc);
             // the bias part of the geo block: b_last[1+k] * sum_s pbar[c]
             const float* Bl = a.f.theta + a.net.gb_off[K - 1];

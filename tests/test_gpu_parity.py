@@ -81,15 +81,14 @@ def test_render_forward_backward_matches_oracle(dataset, n_levels, layers, n_sam
 
 
 @pytest.mark.parametrize("dataset,n_levels,layers,n_samples,n_rays,dual,tol", [
-    ("DTU", 16, (None, 64, 64, 64, 16), 128, 300, False, 1e-4),   # config 2 networks; 76 800 samples: every CTA walks several tiles
-    ("bmvs", 16, (None, 64, 16), 47, 33, True, 1e-3),             # dual field, ragged tile tail (3 102 samples: below the auto threshold)
-    ("DTU", 4, (None, 64, 16), 64, 16, False, 1e-3),
+    ("DTU", 16, (None, 64, 64, 64, 16), 128, 300, False, 2e-4),   # config 2 networks; 76 800 samples: every CTA walks several tiles
+    ("bmvs", 16, (None, 64, 16), 47, 33, True, 2e-4),             # dual field, ragged tile tail (3 102 samples: below the auto threshold)
+    ("DTU", 4, (None, 64, 16), 64, 16, False, 2e-4),
 ])
 def test_tensor_core_backward_matches_simt_backward(dataset, n_levels, layers, n_samples, n_rays, dual, tol):
     """ls2fm_field_backward_tc (tcgen05: 2-channel stacked tiles, streamed weights, all weight gradients in TMEM) against
-    ls2fm_field_backward_simt (fp32 FMA pipes) on identical inputs.  Every product on the gradient path is 3xTF32 (fp32-level);
-    the weight gradients round their layer-input operand to tf32, an unbiased 2^-12 per term that averages out over the rows --
-    hence the looser bound on the launches that are smaller than what the library sends to this kernel by itself."""
+    ls2fm_field_backward_simt (fp32 FMA pipes) on identical inputs.  Every product, weight gradients included, is 3xTF32
+    (fp32-level), so the two agree to ~1e-5 of each gradient's scale."""
     from levels2fm_b200 import ops
     res = {}
     for simt in (True, False):
