@@ -48,9 +48,26 @@ static int ls_max_smem() {
     }
     return n;
 }
+// opt in to > 48 KB of dynamic shared memory, once per (kernel, device, size): the attribute call costs microseconds of host time
+// in front of every launch otherwise (one process drives one GPU, but the cache is keyed by device all the same)
 template <class K> static int ls_opt_in_smem(K kernel, int bytes) {
+    struct Entry { const void* fn; int dev; int bytes; };
+    static thread_local Entry cache[64];
+    static thread_local int n_cache = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void* key = reinterpret_cast<const void*>(kernel);
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].fn == key && cache[i].dev == dev) {
+            if (cache[i].bytes >= bytes) return 0;
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (e != cudaSuccess) return ls_fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+            cache[i].bytes = bytes;
+            return 0;
+        }
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return ls_fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    if (n_cache < 64) cache[n_cache++] = Entry{key, dev, bytes};
     return 0;
 }
 static int ls_check_launch(const char* what) {
