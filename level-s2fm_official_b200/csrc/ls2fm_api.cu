@@ -328,9 +328,19 @@ int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, c
         LS_LAUNCH(ls_field_sdf_tc_kernel, (unsigned)grid, LS_TC_THREADS, csmem, stream, a, cnet, net);
         return ls_check_launch("field_forward(sdf)");
     }
-    if (ls_opt_in_smem(ls_field_forward_tc_kernel, smem)) return 1;
     int64_t grid = n_tiles < ls_sm_count() ? n_tiles : ls_sm_count();
-    LS_LAUNCH(ls_field_forward_tc_kernel, (unsigned)grid, LS_TC_THREADS, smem, stream, a, net);
+    bool ring_ok = field->tc_image != nullptr;      // streamed weights: every half-matrix must fit a ring slot
+    for (int l = 0; l < field->n_layers; ++l) ring_ok = ring_ok && net.n_out_pad[l] * net.k_in_pad[l] <= LS_TC_RING_SLOT;
+    for (int l = 0; l < field->n_layers - 1; ++l) ring_ok = ring_ok && net.n_in_pad[l] * LS_H <= LS_TC_RING_SLOT;
+    if (ring_ok) {
+        const LsTcNet rnet = ls_plan_tc_ring(*field, rad ? rad->in_dim : 0);
+        const int rsmem = rnet.total * (int)sizeof(float);
+        if (ls_opt_in_smem(ls_field_forward_tc_kernel<true>, rsmem)) return 1;
+        LS_LAUNCH(ls_field_forward_tc_kernel<true>, (unsigned)grid, LS_TC_THREADS, rsmem, stream, a, rnet, net);
+    } else {
+        if (ls_opt_in_smem(ls_field_forward_tc_kernel<false>, smem)) return 1;
+        LS_LAUNCH(ls_field_forward_tc_kernel<false>, (unsigned)grid, LS_TC_THREADS, smem, stream, a, net, net);
+    }
     return ls_check_launch("field_forward");
 }
 

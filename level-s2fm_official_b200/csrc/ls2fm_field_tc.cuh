@@ -32,6 +32,7 @@ struct LsTcNet {
     int weff, rad_pitch;
     int misc;            // mbarrier + tmem slot
     int red;             // [4][128][3] x 2 cross-column-group reduction scratch (normal, colour)
+    int ring;            // streamed-weights variant: 3 slots of LS_TC_RING_SLOT floats
     int total;           // floats
     // image-only extension (global memory, never part of the forward kernels' shared-memory copy): the output layer as a
     // transposed operand B[n = hidden unit][k = output], hi then lo, for the reverse pass of the tensor-core backward kernel
@@ -72,6 +73,46 @@ inline LsTcNet ls_plan_tc(const ls2fm_field_t& f, int rad_in_dim, bool with_tran
     n.wtl_lo = n.wtl_hi + LS_H * n.kl_pad;
     n.image_total = n.wtl_lo + LS_H * n.kl_pad;
     return n;
+}
+
+// Shared-memory plan of the streamed-weights forward kernel: only biases, W_last[0,:], W_eff, the reduction scratch and a 3-slot
+// ring of 16 KB half-matrices (hi or lo) live in shared memory -- ~60 KB instead of 207 KB, and the hardware hands the rest to L1,
+// which is what the hash gather wants.  Matrix offsets (w_hi, wt_hi, ...) of this plan are NOT used: they come from the image plan.
+constexpr int LS_TC_RING_SLOT = 4096;
+inline LsTcNet ls_plan_tc_ring(const ls2fm_field_t& f, int rad_in_dim) {
+    LsTcNet n = ls_plan_tc(f, rad_in_dim);
+    int off = 0;
+    for (int l = 0; l < f.n_layers; ++l) { n.bias[l] = off; off += LS_H; }
+    n.wlast0 = off; off += LS_H;
+    n.weff = off; off += 3 * n.rad_pitch + 4;
+    n.misc = ls_round4(off); off = n.misc + 16;        // +0 MMA barrier, +2/+4/+6 ring barriers, +12 TMEM slot
+    n.red = off; off += 2 * 4 * LS_TC_M * 3;
+    n.ring = ls_round_up(off, 32); off = n.ring + 3 * LS_TC_RING_SLOT;
+    n.total = off;
+    return n;
+}
+// biases, W_last[0, :] and W_eff straight from theta (the streamed-weights kernel keeps nothing else resident)
+LS_DEV void ls_stage_small_tc(const LsFieldArgs& a, const LsTcNet& net, float* smem, int tid, int nt) {
+    const int K = a.f.n_layers;
+    for (int l = 0; l < K; ++l) {
+        const int dout = a.f.dims[l + 1];
+        const float* Bg = a.f.theta + a.net.gb_off[l];
+        for (int e = tid; e < LS_H; e += nt) smem[net.bias[l] + e] = e < dout ? __ldg(Bg + e) : 0.f;
+    }
+    {
+        const int dout = a.f.dims[K];
+        const float* G = a.f.theta + a.net.gw_off[K - 1];
+        for (int e = tid; e < LS_H; e += nt) smem[net.wlast0 + e] = __ldg(G + e * dout);
+    }
+    if (a.r.w_eff) {
+        float* W = smem + net.weff;
+        const int P = net.rad_pitch;
+        for (int e = tid; e < 3 * P; e += nt) {
+            const int c = e / P, i = e - c * P;
+            W[e] = i < a.r.in_dim ? __ldg(a.r.w_eff + c * a.r.in_dim + i) : 0.f;
+        }
+        for (int e = tid; e < 4; e += nt) W[3 * P + e] = e < 3 ? __ldg(a.r.b_eff + e) : 0.f;
+    }
 }
 
 // weights -> shared memory operands (hi/lo, K-major no-swizzle), zero padded
@@ -158,7 +199,10 @@ LS_DEV float ls_softplus_fast(float z, float beta, float inv_beta, float thr) {
 #endif
 }
 
-__global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(const LsFieldArgs a, const LsTcNet net) {
+// RING: the weights stream from the operand image (img: its plan) through a 3-slot ring instead of living in shared memory; one
+// matrix per MMA batch in the order W_0 .. W_{K-1}, W_{H-1}^T .. W_0^T, as hi / lo halves fetched 1-2 batches ahead (cp.async.bulk).
+template <bool RING>
+__global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(const LsFieldArgs a, const LsTcNet net, const LsTcNet img) {
     LS_DYN_SMEM(smem);
     if (ls_n_samples(a.p) == 0) return;          // compacted launch with nothing left (sampler rounds): skip the weight staging
     const int t = threadIdx.x;
@@ -167,7 +211,9 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
     const int K = a.f.n_layers, H = K - 1, L = a.f.n_levels;
     const int din = a.f.dims[0], dout = a.f.dims[K], nh = din - 3;
     const float sp_beta = a.f.softplus_beta, sp_thr = a.f.softplus_threshold, inv_beta = 1.f / a.f.softplus_beta;
-    if (a.f.tc_image) {      // operand image prepared once per step: plain 16-byte copies
+    if (RING) {
+        ls_stage_small_tc(a, net, smem, threadIdx.x, blockDim.x);
+    } else if (a.f.tc_image) {      // operand image prepared once per step: plain 16-byte copies
         const float4* src = reinterpret_cast<const float4*>(a.f.tc_image);
         float4* dst = reinterpret_cast<float4*>(smem);
         for (int e = threadIdx.x; e < net.misc / 4; e += blockDim.x) dst[e] = __ldg(src + e);
@@ -176,9 +222,14 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
     }
     ls_fence_smem_to_async();
     LsTcBar* bar = reinterpret_cast<LsTcBar*>(smem + net.misc);
-    uint32_t* slot = reinterpret_cast<uint32_t*>(smem + net.misc + 4);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(smem + net.misc + (RING ? 12 : 4));
     const uint32_t tmem = ls_tc_alloc(slot);
     ls_tc_bar_init(bar);
+    if (RING) {
+        if (t == 0) { for (int s3 = 0; s3 < 3; ++s3) ls_bar_init1(reinterpret_cast<LsTcBar*>(smem + net.misc + 2 + 2 * s3)); }
+        ls_fence_smem_to_async();
+        __syncthreads();
+    }
     uint32_t phase = 0;
     const bool need_nrm = a.out_nrm != nullptr || a.r.w_eff != nullptr;
     const int colD = H * 128;
@@ -188,6 +239,48 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
 
     const int64_t n_pts = ls_n_samples(a.p);
     const int64_t n_tiles = (n_pts + LS_TC_M - 1) / LS_TC_M;
+    // ---- weight ring (RING): entry e = (batch e >> 1, hi / lo half e & 1) lives in slot e % 3
+    const int NB = 2 * H + 1;
+    const int64_t my_tiles = n_tiles > (int64_t)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_entries = 2 * my_tiles * NB;
+    int64_t gb = 0;
+    auto ring_fetch = [&](int64_t e) {      // one thread
+        if (e < n_entries) {
+            const int b = (int)((e >> 1) % NB);
+            int src, half;
+            if (b < K) { src = img.w_hi[b]; half = img.n_out_pad[b] * img.k_in_pad[b]; }
+            else { const int l = 2 * H - b; src = img.wt_hi[l]; half = img.n_in_pad[l] * LS_H; }
+            const int s3 = (int)(e % 3);
+            ls_bulk_g2s(smem + net.ring + s3 * LS_TC_RING_SLOT, a.f.tc_image + src + (int)(e & 1) * half, half * 4,
+                        reinterpret_cast<LsTcBar*>(smem + net.misc + 2 + 2 * s3));
+        }
+    };
+    auto ring_slot = [&](int64_t e) -> const float* {
+        const int s3 = (int)(e % 3);
+        ls_bar_wait(reinterpret_cast<LsTcBar*>(smem + net.misc + 2 + 2 * s3), (uint32_t)((e / 3) & 1));
+        return smem + net.ring + s3 * LS_TC_RING_SLOT;
+    };
+    if (RING && t == 0) { ring_fetch(0); ring_fetch(1); ring_fetch(2); }
+    // the issuing lane: 3xTF32 batch + commit
+    auto issue = [&](int d_col, int a_hi, int a_lo, const float* w_hi, const float* w_lo, int N, int Kd) {
+        if (RING) {
+            const float* Wh = ring_slot(2 * gb);
+            ls_tc_mma(tmem, d_col, a_lo, Wh, N, Kd, false);
+            ls_tc_mma(tmem, d_col, a_hi, Wh, N, Kd, true);
+            const float* Wl = ring_slot(2 * gb + 1);
+            ls_tc_mma(tmem, d_col, a_hi, Wl, N, Kd, true);
+        } else {
+            ls_tc_mma_x3(tmem, d_col, a_hi, a_lo, w_hi, w_lo, N, Kd);
+        }
+        ls_tc_commit(bar);
+    };
+    auto batch_done = [&]() {
+        ls_tc_wait(bar, phase);
+        if (RING) {
+            if ((t >> 5) == 0) { if (ls_elect()) { ring_fetch(2 * gb + 3); ring_fetch(2 * gb + 4); } }
+            ++gb;
+        }
+    };
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ------------------------------------------------ gather: (sample = row, levels 4cg .. 4cg+3)
         const int64_t i_in = tile * LS_TC_M + row;
@@ -229,11 +322,9 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
         for (int l = 0; l < H; ++l) {
             const int a_hi = l == 0 ? colE_hi : (l - 1) * 128, a_lo = a_hi + 64;
             ls_tc_sync_before_mma();
-            if ((t >> 5) == 0 && ls_elect()) {      // one lane of a converged warp: uniform-register descriptors, back-to-back MMAs
-                ls_tc_mma_x3(tmem, colD, a_hi, a_lo, smem + net.w_hi[l], smem + net.w_lo[l], LS_H, net.k_in_pad[l]);
-                ls_tc_commit(bar);
-            }
-            ls_tc_wait(bar, phase);
+            if ((t >> 5) == 0 && ls_elect())        // one lane of a converged warp: uniform-register descriptors, back-to-back MMAs
+                issue(colD, a_hi, a_lo, smem + net.w_hi[l], smem + net.w_lo[l], LS_H, net.k_in_pad[l]);
+            batch_done();
             const float* bias = smem + net.bias[l] + 16 * cg;
             float v[16], hi[16], lo[16];
             ls_tmem_ld(tmem, colD + 16 * cg, v, 16);
@@ -249,11 +340,9 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
         float y[16];
         {
             ls_tc_sync_before_mma();
-            if ((t >> 5) == 0 && ls_elect()) {      // one lane of a converged warp: uniform-register descriptors, back-to-back MMAs
-                ls_tc_mma_x3(tmem, colD, (H - 1) * 128, (H - 1) * 128 + 64, smem + net.w_hi[K - 1], smem + net.w_lo[K - 1], 32, LS_H);
-                ls_tc_commit(bar);
-            }
-            ls_tc_wait(bar, phase);
+            if ((t >> 5) == 0 && ls_elect())
+                issue(colD, (H - 1) * 128, (H - 1) * 128 + 64, smem + net.w_hi[K - 1], smem + net.w_lo[K - 1], 32, LS_H);
+            batch_done();
 #pragma unroll
             for (int q = 0; q < 16; ++q) y[q] = 0.f;
             const float* bias = smem + net.bias[K - 1];
@@ -283,11 +372,9 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
             }
             for (int l = H - 1; l >= 0; --l) {
                 ls_tc_sync_before_mma();
-                if ((t >> 5) == 0 && ls_elect()) {      // one lane of a converged warp: uniform-register descriptors, back-to-back MMAs
-                    ls_tc_mma_x3(tmem, colD, l * 128, l * 128 + 64, smem + net.wt_hi[l], smem + net.wt_lo[l], net.n_in_pad[l], LS_H);
-                    ls_tc_commit(bar);
-                }
-                ls_tc_wait(bar, phase);
+                if ((t >> 5) == 0 && ls_elect())
+                    issue(colD, l * 128, l * 128 + 64, smem + net.wt_hi[l], smem + net.wt_lo[l], net.n_in_pad[l], LS_H);
+                batch_done();
                 if (l > 0) {
                     const int cA = (l - 1) * 128 + 16 * cg;
                     float v[16], ah[16], al[16], hi[16], lo[16];

@@ -193,7 +193,8 @@ def test_fused_sphere_trace_kernel_internals():
 @pytest.mark.parametrize("n_levels,layers", [(16, (None, 64, 64, 64, 16)), (16, (None, 64, 16)), (4, (None, 64, 64, 16)), (8, (None, 64, 16))])
 def test_tensor_core_forward_matches_simt_forward_and_operand_image(product_lib, n_levels, layers):
     """The tcgen05 (3xTF32) forward kernel, the fp32-SIMT forward kernel and the prepared-operand-image path are three
-    routes to the same numbers: 1e-5 relative on sdf / features / normals / colours, on ragged sizes."""
+    routes to the same numbers: 1e-5 relative on sdf / features / normals / colours, on ragged sizes.  (With the image the
+    forward kernel keeps no weights in shared memory: they stream through the 3-slot ring, ls_field_forward_tc_kernel<true>.)"""
     from levels2fm_b200 import ops
     opt = common.make_opt("DTU", DEV, n_levels, layers, 32)
     cfg = common.cfg_of(opt, n_levels)
@@ -216,7 +217,8 @@ def test_tensor_core_forward_matches_simt_forward_and_operand_image(product_lib,
     img = ops.field_forward_raw(product_lib, spec, table, theta, pts, rs, image=image, **kw)
     for a, b, c, name in zip(tc, simt, img, ("y", "sdf", "nrm", "rgb")):
         assert common.rel_err(a.cpu(), b.cpu()) < 1e-5, name
-        assert torch.equal(a, c), name + " (operand image)"
+        # with the operand image the weights stream through the ring and the three TF32 terms accumulate in another order
+        assert common.rel_err(a.cpu(), c.cpu()) < 2e-6, name + " (operand image)"
 
 
 def test_fused_render_loss_matches_torch():
