@@ -250,6 +250,7 @@ def main():
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device(dev))
     W = max(args.warmup, 3)
 
