@@ -40,7 +40,7 @@ constexpr int LS_BT_EROWS = 48;                 // feature rows of the encoding 
 constexpr int LS_BT_LBO_E = LS_BT_EROWS * 16 + 16;
 constexpr int LS_BT_LBOF_E = LS_BT_LBO_E / 4;   // 196
 constexpr int LS_BT_SLOT = 4096;                // floats per ring slot (16 KB: the hi OR the lo half of a 64 x 64 operand)
-constexpr int LS_BT_PBP = 17;                   // pitch of a per-sample staging row (odd: conflict-free across the 16 samples of a warp)
+constexpr int LS_BT_PBP = 21;                   // pitch of a per-sample staging row (odd: conflict-free across the 16 samples of a warp)
 // TMEM columns
 constexpr int LS_BT_WG = 0;                     // weight-gradient accumulators: last^T [0,32) | layer 0 [24,72) | layer l [64 l, +64)
 constexpr int LS_BT_A = 192;                    // A_k at LS_BT_A + 64 (k - 1)
@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     //   under B5 of tile n  : the per-sample loads of tile n+1 (position, upstream gradients, saved outputs) -> PBN[next]
     //   under B6 of tile n  : the hash-grid gather of tile n+1 (this thread's two levels) -> 8 registers
     //   under B4 of tile n+1: the hash-table gradient scatter of tile n (adjoints kept in 8 registers, cell from PBN[previous])
-    // PBN row: 0..2 pbar | 3..5 upstream normal gradient | 6..8 position | 9..11 ray direction | 12..14 saved normal | 15 valid
+    // PBN row: 0..2 pbar | 3..5 upstream normal gradient | 6..8 position | 9..11 ray direction | 12..14 saved normal | 15 valid |
+    //          16..18 unit-cube coordinates (computed once here: every gather / scatter piece needs them)
     float* PBN = smem + net.pbn;
     int pb_prev = 2, pb_cur = 0, pb_nxt = 1;
     auto stage_sample = [&](int64_t tile, int buf) {        // raw per-sample loads, spread over the sample's 8 threads
@@ -237,6 +238,9 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                 if (valid) { int ray_id; int64_t io; ls_sample_point(a.p, i, v3, &ray_id, &io); }
                 base = 6;
                 P[15] = valid ? 1.f : 0.f;
+                float u3[3];
+                ls_world_to_unit(a.f.bound_min, a.f.bound_max, v3, u3);
+                P[16] = u3[0]; P[17] = u3[1]; P[18] = u3[2];
             } else if (cg == 1) {
                 if (valid && rad && a.g_rgb) {
 #pragma unroll
@@ -286,9 +290,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     auto gather_piece = [&](int buf, int p) {
         const int r = p >> 1, plane = p & 1;
         const float* P = PBN + (buf * LS_BT_TILE + sl) * LS_BT_PBP;
-        const float x[3] = {P[6], P[7], P[8]};
-        float u[3];
-        ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
+        const float u[3] = {P[16], P[17], P[18]};
         const int l = 4 * cg + 2 * isT + r;
         const float scale = a.f.levels[l].scale;
         const uint32_t res = a.f.levels[l].resolution, size = a.f.levels[l].size, hashed = a.f.levels[l].hashed;
@@ -328,10 +330,9 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     auto scatter_level = [&](int buf, int r, float e0, float e1, float t0, float t1) {
         const float* P = PBN + (buf * LS_BT_TILE + sl) * LS_BT_PBP;
         if (!a.d_table || P[15] == 0.f) return;
-        const float x[3] = {P[6], P[7], P[8]};
-        float u[3], nbar[3];
+        const float u[3] = {P[16], P[17], P[18]};
+        float nbar[3];
         load_nbar(P, nbar);
-        ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
         const int l = 4 * cg + 2 * isT + r;
         const float scale = a.f.levels[l].scale;
         const uint32_t res = a.f.levels[l].resolution, size = a.f.levels[l].size, hashed = a.f.levels[l].hashed;
