@@ -384,7 +384,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_DESC[args.workload], "rays_per_gpu": RAYS_PER_GPU, "samples_per_ray": int(n_samples),
                            "regime": args.regime, "l2": "flushed between timed steps (256 MB fill, untimed)",
-                           "parallelism": f"ray-parallel dp{world}, one flat-bucket all-reduce per step"},
+                           "parallelism": f"ray-parallel dp{world}, one flat-bucket all-reduce per step" + (f" ({bucket.collective})" if world > 1 else "")},
                 "clocks": clk, "gpu_launches": launches,
                 "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "roofline": roofline, "loss": float(loss_host[-1])}

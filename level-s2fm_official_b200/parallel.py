@@ -24,11 +24,38 @@ class GradBucket:
     """All parameter gradients as views into one flat fp32 buffer, laid out so the single all-reduce that follows the
     fused backward needs no packing step.  ``extra`` floats at the tail carry loss sums / counts."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 8):
+    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 8, symmetric: bool = False):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(total + extra, dtype=torch.float32, device=dev)
+        extra += (-(total + extra)) % 4          # whole 16-byte words: what the multimem reduction moves
+        self.flat = None
+        self.group_name = None      # set when the bucket lives in symmetric memory and the NVSwitch can reduce it (NVLS multicast)
+        if (symmetric and dev.type == "cuda" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                and dist.get_backend() == "nccl"):
+            # One process per GPU on one NVSwitch box: put the bucket in symmetric memory and let the switch do the sum
+            # (multimem.ld_reduce / multimem.st: every GPU reads 1/N of the bucket reduced in the switch and broadcasts it) --
+            # measured on 8 B200s for this 48.9 MB bucket: 0.13 ms vs 0.22 ms for ncclAllReduce (tools/allreduce_probe.py).
+            # OPT-IN for now: inside the full step at 2 GPUs the symmetric-memory bucket was slower end to end (3.76 vs 3.53 ms
+            # per step) and the GPU budget of round 1 ran out before the 8-GPU step could be measured with it.
+            try:
+                import torch.distributed._symmetric_memory as symm
+                flat = symm.empty(total + extra, dtype=torch.float32, device=dev)
+                hdl = symm.rendezvous(flat, dist.group.WORLD.group_name)
+                if getattr(hdl, "multicast_ptr", 0):
+                    # self-test before trusting it: every rank contributes rank + 1, the sum is known
+                    world, gname = dist.get_world_size(), dist.group.WORLD.group_name
+                    flat.fill_(float(dist.get_rank() + 1))
+                    torch.ops.symm_mem.multimem_all_reduce_(flat, "sum", gname)
+                    ok = torch.tensor([float(bool((flat == world * (world + 1) / 2).all()))], device=dev)
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                    if bool(ok.item()):
+                        flat.zero_()
+                        self.flat, self.group_name = flat, gname
+            except Exception:
+                self.flat, self.group_name = None, None
+        if self.flat is None:
+            self.flat = torch.zeros(total + extra, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -48,5 +75,12 @@ class GradBucket:
 
     def allreduce(self, async_op: bool = False):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            if self.group_name is not None and not async_op:
+                torch.ops.symm_mem.multimem_all_reduce_(self.flat, "sum", self.group_name)
+                return None
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
         return None
+
+    @property
+    def collective(self) -> str:
+        return "NVLS multimem all-reduce (symmetric memory)" if self.group_name is not None else "ncclAllReduce"
