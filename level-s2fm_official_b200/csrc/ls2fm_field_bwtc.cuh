@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     //   under B5 of tile n  : the per-sample loads of tile n+1 (position, upstream gradients, saved outputs) -> PBN[next]
     //   under B6 of tile n  : the hash-grid gather of tile n+1 (this thread's two levels) -> 8 registers
     //   under B4 of tile n+1: the hash-table gradient scatter of tile n (adjoints kept in 8 registers, cell from PBN[previous])
-    // PBN row: 0..2 pbar | 3..5 upstream normal gradient | 6..8 position | 9..11 ray direction | 12..14 saved normal | 15 valid |
+    // PBN row: 0..2 pbar | 3..5 nbar (upstream normal gradient incl. the radiance path) | 6..8 position | 9..11 ray direction | 12..14 saved normal | 15 valid |
     //          16..18 unit-cube coordinates (computed once here: every gather / scatter piece needs them)
     float* PBN = smem + net.pbn;
     int pb_prev = 2, pb_cur = 0, pb_nxt = 1;
@@ -250,10 +250,22 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                     }
                 }
                 base = 0;
-            } else if (cg == 2) {
-                if (valid && a.g_nrm) {
+            } else if (cg == 2) {       // nbar = upstream normal gradient + W_eff[:, 3:6]^T pbar (its own copy of pbar: no barrier needed)
+                if (valid) {
+                    float pb[3] = {0.f, 0.f, 0.f};
+                    if (rad && a.g_rgb) {
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) v3[d] = __ldg(a.g_nrm + 3 * i + d);
+                        for (int c = 0; c < 3; ++c) {
+                            const float rgb = __ldg(a.saved_rgb + 3 * i + c);
+                            pb[c] = __ldg(a.g_rgb + 3 * i + c) * rgb * (1.f - rgb);
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        float v = a.g_nrm ? __ldg(a.g_nrm + 3 * i + d) : 0.f;
+                        if (rad) v += Weff[3 + d] * pb[0] + Weff[RP + 3 + d] * pb[1] + Weff[2 * RP + 3 + d] * pb[2];
+                        v3[d] = v;
+                    }
                 }
                 base = 3;
             } else {
@@ -273,15 +285,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         }
         if (base >= 0) { P[base] = v3[0]; P[base + 1] = v3[1]; P[base + 2] = v3[2]; }
     };
-    // nbar = upstream normal gradient + W_eff[:, 3:6]^T pbar
-    auto load_nbar = [&](const float* P, float (&nbar)[3]) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            float v = P[3 + d];
-            if (rad) v += Weff[3 + d] * P[0] + Weff[RP + 3 + d] * P[1] + Weff[2 * RP + 3 + d] * P[2];
-            nbar[d] = v;
-        }
-    };
+    auto load_nbar = [&](const float* P, float (&nbar)[3]) { nbar[0] = P[3]; nbar[1] = P[4]; nbar[2] = P[5]; };
     float e4[4], d4[4];                 // gather in flight (next tile)
     float pl[2][3];                     // ... its z = 0 plane of the level being evaluated: value, d/dx, d/dy per feature
     // The gather of a tile is cut into four pieces, one per tensor-core batch it hides under: piece p = (level r = p >> 1 of this

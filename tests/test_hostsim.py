@@ -77,6 +77,40 @@ def test_tensor_core_backward_agrees_with_simt_backward():
         assert common.rel_err(a, b) < 5e-5, (k, common.rel_err(a, b))
 
 
+def test_forced_tensor_core_backward_refuses_what_it_cannot_do(hostsim_lib):
+    """ls2fm_field_backward_tc is strict: without the operand image (its weights stream from it) or without a gradient on the
+    normals it reports an error instead of silently running something else."""
+    from levels2fm_b200 import ops
+    opt = common.make_opt("DTU", "cpu", 4, (None, 64, 16), 16)
+    sdf, _, _ = common.build_models(opt)
+    spec, table = sdf.field_spec(), sdf.table().detach()
+    theta = sdf.SDF_MLP.theta().detach().contiguous()
+    x = torch.rand(70, 3) * 1.6 - 0.8
+    pts = ops._points(hostsim_lib, x.contiguous(), None, None, None)
+    g = torch.ones(70)
+    d_table, d_theta = torch.zeros_like(table), torch.zeros_like(theta)
+    gn0 = torch.ones(70, 3)
+
+    def forced_tc(image, g_nrm):
+        f = spec.c_field(hostsim_lib, table, theta, image)
+        ops._call(hostsim_lib, "field_backward_tc", hostsim_lib.dll.ls2fm_field_backward_tc, f, pts, None, None, hostsim_lib.ptr(g),
+                  hostsim_lib.ptr(g_nrm), None, None, None, hostsim_lib.ptr(d_table), hostsim_lib.ptr(d_theta), None, None, None,
+                  hostsim_lib.stream())
+
+    with pytest.raises(RuntimeError, match="field_backward_tc"):      # no operand image
+        forced_tc(None, gn0)
+    image = ops.field_prepare_raw(hostsim_lib, spec, table, theta, None)
+    with pytest.raises(RuntimeError, match="field_backward_tc"):      # image, but first-order only (no gradient on the normals)
+        forced_tc(image, None)
+    assert float(d_table.abs().max()) == 0.0 and float(d_theta.abs().max()) == 0.0      # refused launches wrote nothing
+    # and with both it agrees with the SIMT kernel
+    gn = torch.randn(70, 3)
+    ops.field_backward_raw(hostsim_lib, spec, table, theta, pts, None, None, g, gn, None, None, None, d_table, d_theta, image=image, mode="tc")
+    d_table2, d_theta2 = torch.zeros_like(table), torch.zeros_like(theta)
+    ops.field_backward_raw(hostsim_lib, spec, table, theta, pts, None, None, g, gn, None, None, None, d_table2, d_theta2, mode="simt")
+    assert common.rel_err(d_table, d_table2) < 5e-5 and common.rel_err(d_theta, d_theta2) < 5e-5
+
+
 def test_golden_c1_through_kernels():
     gold = gc.load("c1_render.npz")
     out, grads, loss = gc.run_c1_product(gold, "cpu")
