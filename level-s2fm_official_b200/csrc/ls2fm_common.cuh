@@ -20,6 +20,7 @@
 #define LS_LAUNCH(kernel, grid, block, smem, stream, ...) \
     simt::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kernel(__VA_ARGS__); })
 #define LS_FAST_EXP(x) expf(x)
+#define LS_NOINLINE
 #else
 #include <cuda_runtime.h>
 #define LS_HD __host__ __device__ __forceinline__
@@ -28,6 +29,7 @@
 #define LS_LAUNCH(kernel, grid, block, smem, stream, ...) \
     kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define LS_FAST_EXP(x) __expf(x)
+#define LS_NOINLINE __device__ __noinline__
 #endif
 
 // ---------------------------------------------------------------- constants
@@ -89,6 +91,42 @@ LS_DEV uint32_t ls_corner_index(uint32_t resolution, uint32_t size, uint32_t has
     // point inside the box, so the (exact) modulo only runs for out-of-range coordinates.
     if (hashed && (size & (size - 1)) == 0) return index & (size - 1);
     return index < size ? index : index % size;
+}
+
+// All corner indices of a cell (or the 4 of one z-plane: corners first .. first + N - 1), deciding the path ONCE per level instead of
+// once per corner: hashed power-of-two levels and in-range cells of dense levels are branch-free; anything else (out-of-range
+// coordinates, odd table sizes) takes ls_corner_index corner by corner.  Bit-identical to ls_corner_index by construction: the
+// same uint32 expressions, and for an in-range dense cell every index is < resolution^3 <= size, so tcnn's "% size" is the identity.
+// (out of line: the rare path must not be replicated into every gather / scatter site of the big kernels)
+LS_NOINLINE uint32_t ls_corner_index_slow(uint32_t resolution, uint32_t size, uint32_t hashed, uint32_t g0, uint32_t g1, uint32_t g2, int corner) {
+    LsCell c;
+    c.g[0] = g0; c.g[1] = g1; c.g[2] = g2;
+    c.w[0] = c.w[1] = c.w[2] = 0.f;
+    return ls_corner_index(resolution, size, hashed, c, corner);
+}
+template <int FIRST, int N>
+LS_DEV void ls_corner_indices(uint32_t resolution, uint32_t size, uint32_t hashed, const LsCell& c, uint32_t (&idx)[N]) {
+    if (hashed && (size & (size - 1)) == 0) {
+        const uint32_t m = size - 1;
+        const uint32_t y0 = c.g[1] * 2654435761u, y1 = (c.g[1] + 1) * 2654435761u;
+        const uint32_t z0 = c.g[2] * 805459861u, z1 = (c.g[2] + 1) * 805459861u;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int corner = FIRST + k;
+            idx[k] = ((c.g[0] + (corner & 1)) ^ ((corner & 2) ? y1 : y0) ^ ((corner & 4) ? z1 : z0)) & m;
+        }
+    } else if (!hashed && c.g[0] < resolution - 1 && c.g[1] < resolution - 1 && c.g[2] < resolution - 1) {
+        const uint32_t r2 = resolution * resolution;
+        const uint32_t base = c.g[0] + c.g[1] * resolution + c.g[2] * r2;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int corner = FIRST + k;
+            idx[k] = base + (corner & 1) + ((corner & 2) ? resolution : 0u) + ((corner & 4) ? r2 : 0u);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) idx[k] = ls_corner_index_slow(resolution, size, hashed, c.g[0], c.g[1], c.g[2], FIRST + k);
+    }
 }
 
 // world -> unit cube exactly as models/base.py:35: (x - bmin) / (bmax - bmin)

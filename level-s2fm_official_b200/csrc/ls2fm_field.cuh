@@ -225,7 +225,10 @@ LS_DEV void ls_level_eval(const ls2fm_field_t& f, int l, const float u[3], float
     const LsCell c = ls_cell(scale, u);
     float2 v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float2*>(tab) + ls_corner_index(res, size, hashed, c, k));
+    uint32_t ci[8];
+    ls_corner_indices<0, 8>(res, size, hashed, c, ci);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float2*>(tab) + ci[k]);
     const float w0 = c.w[0], w1 = c.w[1], w2 = c.w[2];
     const float m0 = 1.f - w0, m1 = 1.f - w1, m2 = 1.f - w2;
 #pragma unroll
@@ -904,6 +907,8 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                     float* tab = a.d_table + 2 * (size_t)a.f.levels[l].offset;
                     const LsCell c = ls_cell(scale, u);
                     const float e0 = ls_el(P, LS_H, 3 + 2 * l, s8), e1 = ls_el(P, LS_H, 3 + 2 * l + 1, s8);
+                    uint32_t ci[8];
+                    ls_corner_indices<0, 8>(res, size, hashed, c, ci);
                     float t0 = 0.f, t1 = 0.f, ns[3] = {0.f, 0.f, 0.f};
                     if (TAN) {
                         t0 = ls_el(Pd, LS_H, 3 + 2 * l, s8); t1 = ls_el(Pd, LS_H, 3 + 2 * l + 1, s8);
@@ -922,8 +927,7 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
                                              ((k & 4) ? ns[2] : -ns[2]) * f0 * f1;
                             g0 += dw * t0; g1 += dw * t1;
                         }
-                        const uint32_t idx = ls_corner_index(res, size, hashed, c, k);
-                        atomicAdd(reinterpret_cast<float2*>(tab) + idx, make_float2(g0, g1));
+                        atomicAdd(reinterpret_cast<float2*>(tab) + ci[k], make_float2(g0, g1));
                     }
                 }
             }

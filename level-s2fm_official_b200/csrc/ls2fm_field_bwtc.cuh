@@ -302,7 +302,11 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         const LsCell c = ls_cell(scale, u);
         float2 v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = __ldg(tab + ls_corner_index(res, size, hashed, c, 4 * plane + k));
+        uint32_t ci[4];
+        if (plane) ls_corner_indices<4, 4>(res, size, hashed, c, ci);
+        else ls_corner_indices<0, 4>(res, size, hashed, c, ci);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(tab + ci[k]);
         const float w0 = c.w[0], w1 = c.w[1], w2 = c.w[2];
         const float m0 = 1.f - w0, m1 = 1.f - w1, m2 = 1.f - w2;
         float nbar[3];
@@ -345,6 +349,8 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         float ns[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) ns[d] = nbar[d] * scale * a.inv_ext[d];
+        uint32_t ci[8];
+        ls_corner_indices<0, 8>(res, size, hashed, c, ci);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float f0 = (k & 1) ? c.w[0] : 1.f - c.w[0];
@@ -353,8 +359,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
             const float wgt = f0 * f1 * f2;
             const float dw = ((k & 1) ? ns[0] : -ns[0]) * f1 * f2 + ((k & 2) ? ns[1] : -ns[1]) * f0 * f2 +
                              ((k & 4) ? ns[2] : -ns[2]) * f0 * f1;
-            const uint32_t idx = ls_corner_index(res, size, hashed, c, k);
-            atomicAdd(reinterpret_cast<float2*>(tab) + idx, make_float2(wgt * e0 + dw * t0, wgt * e1 + dw * t1));
+            atomicAdd(reinterpret_cast<float2*>(tab) + ci[k], make_float2(wgt * e0 + dw * t0, wgt * e1 + dw * t1));
         }
     };
     const bool has_levels = 4 * cg < L;

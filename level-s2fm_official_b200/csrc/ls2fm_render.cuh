@@ -235,9 +235,11 @@ __global__ void ls_grid_encode_kernel(const ls2fm_field_t f, const float* __rest
     const uint32_t res = f.levels[l].resolution, size = f.levels[l].size, hashed = f.levels[l].hashed, off = f.levels[l].offset;
     const LsCell c = ls_cell(scale, uu);
     float h0 = 0.f, h1 = 0.f;
-#pragma unroll
+    uint32_t ci[8];
+    ls_corner_indices<0, 8>(res, size, hashed, c, ci);      // (the index hook of the bit-exactness tests goes through the same code
+#pragma unroll                                              //  as the field kernels' gathers)
     for (int k = 0; k < 8; ++k) {
-        const uint32_t idx = ls_corner_index(res, size, hashed, c, k);
+        const uint32_t idx = ci[k];
         if (idx_out) idx_out[(i * L + l) * 8 + k] = off + idx;
         const float2 v = __ldg(reinterpret_cast<const float2*>(f.table) + off + idx);
         const float wgt = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) * ((k & 4) ? c.w[2] : 1.f - c.w[2]);
