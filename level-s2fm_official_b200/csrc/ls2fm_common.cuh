@@ -28,7 +28,11 @@
 #define LS_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
 #define LS_LAUNCH(kernel, grid, block, smem, stream, ...) \
     kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
-#define LS_FAST_EXP(x) __expf(x)
+// MUFU-rate exp / log without __expf's denormal-range fix-up (two extra predicated multiplies and a compare per call): arguments
+// below -126 flush to 0, which is what every user here wants (exp of a large negative number inside 1 - e, 1 + e, e / (1 + e)).
+__device__ __forceinline__ float ls_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ls_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#define LS_FAST_EXP(x) ls_ex2((x) * 1.4426950408889634f)
 #define LS_NOINLINE __device__ __noinline__
 #endif
 

@@ -482,18 +482,22 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                 const float zd = isT ? xv[8 + k] : r;            // tangent pre-activation
                 if (l > 0) z += bias[k];                         // (layer 0: the bias rides on the ones column)
                 const float bz = z * sp_beta;
+#if defined(LS_HOSTSIM)
                 if (bz > sp_thr) { av[k] = z; dv[k] = zd; }
                 else {
-#if defined(LS_HOSTSIM)
                     const float e = expf(bz);
                     av[k] = log1pf(e) * inv_beta;
                     dv[k] = zd * (e / (e + 1.f));
-#else
-                    const float e = __expf(bz);
-                    av[k] = __logf(1.f + e) * inv_beta;
-                    dv[k] = zd * __fdividef(e, e + 1.f);
-#endif
                 }
+#else
+                // branch-free (see ls_softplus_fast): phi = log(1 + e) / beta, phi' = e / (1 + e), threshold zone by select
+                const float e = ls_ex2(fminf(bz, sp_thr) * 1.4426950408889634f);
+                const float e1 = 1.f + e;
+                const float soft = ls_lg2(e1) * (0.6931471805599453f * inv_beta);
+                const float dphi = __fdividef(e, e1);
+                av[k] = bz > sp_thr ? z : soft;
+                dv[k] = bz > sp_thr ? zd : zd * dphi;
+#endif
             }
             float out[16], lo[16];
 #pragma unroll

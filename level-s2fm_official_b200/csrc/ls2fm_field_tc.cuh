@@ -195,7 +195,11 @@ LS_DEV float ls_softplus_fast(float z, float beta, float inv_beta, float thr) {
 #if defined(LS_HOSTSIM)
     return bz > thr ? z : log1pf(expf(bz)) * inv_beta;
 #else
-    return bz > thr ? z : __logf(1.f + __expf(bz)) * inv_beta;
+    // branch-free: the exponential is evaluated for every element (argument clamped at the threshold) and the threshold zone is a
+    // select -- a per-element branch costs BSSY/BRA/BSYNC plus the serialisation of mixed warps, more than the two MUFU ops it skips
+    const float e = ls_ex2(fminf(bz, thr) * 1.4426950408889634f);
+    const float s = ls_lg2(1.f + e) * (0.6931471805599453f * inv_beta);
+    return bz > thr ? z : s;
 #endif
 }
 
