@@ -372,7 +372,7 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
         const LsBtNet net = ls_plan_bt(*field, with_rad ? rad->in_dim : 0);
         const int smem = net.total * (int)sizeof(float);
         bool fits = smem <= ls_max_smem() && img.k_in_pad[0] <= LS_BT_EROWS && img.n_in_pad[0] <= LS_BT_EROWS;
-        if (with_rad) fits = fits && 3 * (rad->in_dim - rad->k_geo) + 3 <= 160;      // W_eff-gradient reducers: the last five warps
+        if (with_rad) fits = fits && 3 * (3 * (rad->in_dim - rad->k_geo) + 3) <= LS_BT_THREADS;      // W_eff-gradient reducers: 3 sample ranges per pair
         for (int l = 0; l < KL - 1; ++l) fits = fits && img.n_out_pad[l] * img.k_in_pad[l] <= LS_BT_SLOT && img.n_in_pad[l] * LS_H <= LS_BT_SLOT;
         if (fits) {
             a.net = ls_plan_net(*field, with_rad ? rad->in_dim : 0, 1, false);        // theta offsets

@@ -454,15 +454,20 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                     ls_tc_commit(bar);
                 }
             }
-            if (rad && l == 0 && t >= LS_BT_THREADS - 160 && t - (LS_BT_THREADS - 160) < 3 * nin + 3) {
-                // W_eff / b_eff gradient of this tile (RIN / PB were completed before this batch's barrier), by the last five warps
-                const int tt = t - (LS_BT_THREADS - 160);
+            if (rad && l == 0 && t < 3 * (3 * nin + 3)) {
+                // W_eff / b_eff gradient of this tile (RIN / PB were completed before this batch's barrier): (channel, input) pairs x
+                // three sample ranges spread over the whole CTA, so no warp carries a 64-long dependent chain into the next barrier
+                const int n_items = 3 * nin + 3;
+                const int part = t / n_items, tt = t - part * n_items;
                 const int c = tt < 3 * nin ? tt / nin : tt - 3 * nin;
                 const int idx = tt < 3 * nin ? tt - c * nin : -1;
-                float acc = 0.f;
-#pragma unroll 4
-                for (int s = 0; s < LS_BT_TILE; ++s) acc = fmaf(PB[4 * s + c], idx >= 0 ? RIN[s * nin + idx] : 1.f, acc);
-                weff_acc += acc;
+                const int s0 = part * 22, s1 = s0 + 22 < LS_BT_TILE ? s0 + 22 : LS_BT_TILE;
+                float acc0 = 0.f, acc1 = 0.f;
+                for (int s = s0; s + 1 < s1; s += 2) {      // (22, 22 and 20 samples: all even)
+                    acc0 = fmaf(PB[4 * s + c], idx >= 0 ? RIN[s * nin + idx] : 1.f, acc0);
+                    acc1 = fmaf(PB[4 * s + 4 + c], idx >= 0 ? RIN[(s + 1) * nin + idx] : 1.f, acc1);
+                }
+                weff_acc += acc0 + acc1;
             }
             if (l == H - 1 && has_next) stage_sample(tile + gridDim.x, pb_nxt);     // next tile's per-sample loads run under this batch
             if (sc_pending && has_levels) {     // the previous tile's table-gradient scatter runs under this batch
@@ -753,7 +758,8 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     }
     if (rad && a.d_w_eff && my_tiles > 0) {
         const int in_dim = a.r.in_dim;
-        const int tt = t - (LS_BT_THREADS - 160);
+        const int n_items = 3 * nin + 3;
+        const int tt = t < 3 * n_items ? t % n_items : -1;         // three sample-range partials per (channel, input) pair
         if (tt >= 0 && tt < 3 * nin) {
             const int c = tt / nin, idx = tt - c * nin;
             atomicAdd(a.d_w_eff + c * in_dim + (idx < o_geo ? idx : idx + kg), weff_acc);
