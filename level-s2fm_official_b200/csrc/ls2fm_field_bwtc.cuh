@@ -301,7 +301,6 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         const float2* tab = reinterpret_cast<const float2*>(a.f.table) + a.f.levels[l].offset;
         const LsCell c = ls_cell(scale, u);
         float2 v[4];
-#pragma unroll
         uint32_t ci[4];
         if (plane) ls_corner_indices<4, 4>(res, size, hashed, c, ci);
         else ls_corner_indices<0, 4>(res, size, hashed, c, ci);
