@@ -20,12 +20,20 @@
 //     IS the contraction over the stacked rows.  The output layer's gradient is accumulated transposed (M = hidden unit) with
 //     three extra columns carrying the radiance pre-activation gradient, which yields the geo-feature block of dL/dW_eff
 //     without ever computing the output layer in this kernel.
-//   * weights: W_l (forward) and W_l^T (reverse) as hi/lo K-major operands would need 200 KB; they stream instead from the
-//     L2-resident operand image (ls2fm_field_prepare) through a 2-slot ring of 32 KB with cp.async.bulk + mbarrier, one
-//     matrix per MMA batch, fetched two batches ahead by the issuing thread.
-//   * per tile: H forward batches, 1 + H reverse batches (each reverse batch = weight gradient of one layer + the transposed
-//     product into the layer below); no output-layer forward, no separate bias pass (layer 0's bias gradient rides on the
-//     ones column of the encoding, the others are column sums of the staged adjoints).
+//   * weights: W_l (forward) and W_l^T (reverse) as hi/lo K-major operands would need 200 KB (tf32 operands cannot be read
+//     transposed: every MN-major descriptor variant returns zeros, tools/probe/tc_probe4.cu); they stream instead from the
+//     L2-resident operand image (ls2fm_field_prepare) through a 3-slot ring of 16 KB half-matrices (hi, then lo) with
+//     cp.async.bulk + mbarrier, one matrix per MMA batch, fetched one to two batches ahead by the issuing lane.
+//   * MMA issue: one elect.sync lane of the converged warp 0 (uniform-register descriptors, back-to-back UTCHMMA).
+//   * per tile: H forward batches, 1 + H reverse batches.  A reverse batch commits the product into the layer below first
+//     (critical path, mbarrier `bar`) and the layer's weight-gradient MMAs second on their own mbarrier (`bar2`), which is only
+//     waited for before the staging arrays are rewritten.  No output-layer forward, no separate bias pass (layer 0's bias
+//     gradient rides on the ones column of the encoding, the hidden layers' are 15-shuffle column sums of the adjoints, the
+//     output layer's are per-thread partial sums).
+//   * cross-tile software pipeline, same warps: the next tile's per-sample loads (PBN, 3 tiles deep) run under the last forward
+//     batch, its hash gather -- four z-plane pieces of four corner loads -- under B5 and the reverse batches, and the previous
+//     tile's table-gradient scatter (adjoints parked in 8 registers) under the next tile's forward batches.
+//   * shared memory: staging 4 x 33 KB | encoding stash 25 KB | PBN 16 KB | ring 48 KB | biases, W_eff, barriers: 226 KB.
 #pragma once
 
 #include "ls2fm_field_tc.cuh"
