@@ -63,6 +63,28 @@ LS_DEV float ls_softplus(float z, float beta, float thr) {
 // ex2.approx based: absolute error ~1e-7 on a value in [0, 1] -- fp32 rounding level for everything downstream.
 LS_DEV float ls_softplus_d1_from_a(float a, float beta) { return 1.f - LS_FAST_EXP(-beta * a); }
 LS_DEV float ls_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// The tensor-core kernels' versions of the radiance tail: same functions on the MUFU units.
+//   sin / cos: Cody-Waite reduction to [-pi, pi] (2 pi = hi + lo, both fma'd), then sin.approx / cos.approx: |error| < 5e-7 for the
+//   arguments of the view-direction embedding (|v| 2^k < 16) -- sinf / cosf cost ~40 instructions each with a slow-path branch and
+//   sat in only half of the warps (the Fourier lanes), holding everybody up at the next barrier.
+//   sigmoid: ex2.approx + fast reciprocal, relative error ~2e-7.
+LS_DEV void ls_sincos_fast(float x, float* s, float* c) {
+#if defined(LS_HOSTSIM)
+    *s = sinf(x); *c = cosf(x);
+#else
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, x);
+    r = fmaf(k, 1.7484555e-7f, r);
+    *s = __sinf(r); *c = __cosf(r);
+#endif
+}
+LS_DEV float ls_sigmoid_fast(float x) {
+#if defined(LS_HOSTSIM)
+    return 1.f / (1.f + expf(-x));
+#else
+    return __fdividef(1.f, 1.f + ls_ex2(-1.4426950408889634f * x));
+#endif
+}
 
 // ---------------------------------------------------------------- hash grid (tcnn GridEncoding) [EXT]
 struct LsCell {

@@ -443,8 +443,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
                         const float ang = Pc[9 + d] * fr;
-                        in[9 + 6 * k + d] = sinf(ang);
-                        in[12 + 6 * k + d] = cosf(ang);
+                        ls_sincos_fast(ang, &in[9 + 6 * k + d], &in[12 + 6 * k + d]);
                     }
                 }
             }
@@ -586,8 +585,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         for (int k = H; k >= 1; --k) {
             const int colA = LS_BT_A + 64 * (k - 1);
             float dvv[16], avv[16];
-            ls_tmem_ld(tmem, LS_BT_D + 16 * cg, dvv, 16);
-            ls_tmem_ld(tmem, colA + 16 * cg, avv, 16);
+            ls_tmem_ld2x16(tmem, LS_BT_D + 16 * cg, dvv, colA + 16 * cg, avv);       // both in flight, one wait
             float zb[8], zd[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {

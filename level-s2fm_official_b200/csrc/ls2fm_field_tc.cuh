@@ -367,8 +367,7 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
                 const float* wl = smem + net.wlast0 + 16 * cg;
                 const int cA = (H - 1) * 128 + 16 * cg;
                 float ah[16], al[16], hi[16], lo[16];
-                ls_tmem_ld(tmem, cA, ah, 16);
-                ls_tmem_ld(tmem, cA + 64, al, 16);
+                ls_tmem_ld2x16(tmem, cA, ah, cA + 64, al);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) ls_split_tf32(ls_softplus_d1_from_a(ah[q] + al[q], sp_beta) * (a.s * wl[q]), hi[q], lo[q]);
                 ls_tmem_st(tmem, cA, hi, 16);
@@ -382,9 +381,8 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
                 if (l > 0) {
                     const int cA = (l - 1) * 128 + 16 * cg;
                     float v[16], ah[16], al[16], hi[16], lo[16];
+                    ls_tmem_ld2x16(tmem, cA, ah, cA + 64, al);
                     ls_tmem_ld(tmem, colD + 16 * cg, v, 16);
-                    ls_tmem_ld(tmem, cA, ah, 16);
-                    ls_tmem_ld(tmem, cA + 64, al, 16);
 #pragma unroll
                     for (int q = 0; q < 16; ++q) ls_split_tf32(ls_softplus_d1_from_a(ah[q] + al[q], sp_beta) * v[q], hi[q], lo[q]);
                     ls_tmem_st(tmem, cA, hi, 16);
@@ -459,7 +457,8 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     const float ang = dir[d] * fr;
-                    const float sn = sinf(ang), cs = cosf(ang);
+                    float sn, cs;
+                    ls_sincos_fast(ang, &sn, &cs);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) pr[c] += W[c * P + o_ray + 3 + 6 * k + d] * sn + W[c * P + o_ray + 6 + 6 * k + d] * cs;
                 }
@@ -477,7 +476,7 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
             if (cg == 0 && valid && a.out_rgb) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    a.out_rgb[3 * i + c] = ls_sigmoid(red_c[row * 3 + c] + red_c[(LS_TC_M + row) * 3 + c] + red_c[(2 * LS_TC_M + row) * 3 + c] +
+                    a.out_rgb[3 * i + c] = ls_sigmoid_fast(red_c[row * 3 + c] + red_c[(LS_TC_M + row) * 3 + c] + red_c[(2 * LS_TC_M + row) * 3 + c] +
                                                       red_c[(3 * LS_TC_M + row) * 3 + c]);
             }
         }

@@ -43,6 +43,7 @@ LS_DEV void ls_tc_bar_init(LsTcBar* b) { if (threadIdx.x == 0) b->arrived = 0; _
 LS_DEV int ls_tc_row() { return (int)(((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31)); }
 LS_DEV void ls_tmem_ld(uint32_t, int col, float* v, int n) { for (int i = 0; i < n; ++i) v[i] = ls_tmem_sim().v[ls_tc_row()][col + i]; }
 LS_DEV void ls_tmem_st(uint32_t, int col, const float* v, int n) { for (int i = 0; i < n; ++i) ls_tmem_sim().v[ls_tc_row()][col + i] = v[i]; }
+LS_DEV void ls_tmem_ld2x16(uint32_t t, int col1, float* v1, int col2, float* v2) { ls_tmem_ld(t, col1, v1, 16); ls_tmem_ld(t, col2, v2, 16); }
 LS_DEV void ls_tc_sync_before_mma() { __syncthreads(); }
 // D[:, d_col + n] (+)= sum_k A[:, a_col + k] * B[n][k]   for n < N, k < K  (called by ONE thread)
 LS_DEV void ls_tc_mma(uint32_t, int d_col, int a_col, const float* B, int N, int K, bool accumulate) {
@@ -132,6 +133,19 @@ LS_DEV void ls_tmem_st8(uint32_t addr, const float* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
                  :: "r"(addr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
                     "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+// two 16-column loads in flight behind ONE tcgen05.wait::ld
+LS_DEV void ls_tmem_ld2x16(uint32_t tmem, int col1, float* v1, int col2, float* v2) {
+    uint32_t r[16], q[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(ls_tmem_lane_addr(tmem, col1)));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
+                   "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]) : "r"(ls_tmem_lane_addr(tmem, col2)));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { v1[i] = __uint_as_float(r[i]); v2[i] = __uint_as_float(q[i]); }
 }
 // n must be a multiple of 8 (compile-time unrolled by the callers)
 LS_DEV void ls_tmem_ld(uint32_t tmem, int col, float* v, int n) {
