@@ -104,6 +104,36 @@ def test_tensor_core_backward_matches_simt_backward(dataset, n_levels, layers, n
         assert common.rel_err(a, b) < tol, (k, common.rel_err(a, b))
 
 
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 200, 9473, 100000])
+def test_tensor_core_backward_ragged_sizes(product_lib, n):
+    """Tile edges of the tcgen05 backward kernel (64-sample tiles, persistent CTAs): a single point, one short of a tile, exactly
+    one, one over, a ragged tail, one tile more than the SM count covers, many -- forced through ls2fm_field_backward_tc and
+    compared with the fp32-SIMT kernel on identical inputs."""
+    from levels2fm_b200 import ops
+    opt = common.make_opt("DTU", DEV, 16, (None, 64, 64, 64, 16), 16)
+    cfg = common.cfg_of(opt, 16)
+    sdf_sd, _ = port.random_state(cfg, seed=4, table_std=0.2)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    spec, table = sdf.field_spec(), sdf.table().detach()
+    theta = sdf.SDF_MLP.theta().detach().contiguous()
+    g = torch.Generator().manual_seed(n)
+    x = (torch.rand(n, 3, generator=g) * 1.6 - 0.8).to(DEV).contiguous()
+    g_sdf, g_nrm = torch.randn(n, generator=g).to(DEV), torch.randn(n, 3, generator=g).to(DEV)
+    pts = ops._points(product_lib, x, None, None, None)
+    image = ops.field_prepare_raw(product_lib, spec, table, theta, None)
+    out = {}
+    for mode in ("tc", "simt"):
+        d_table, d_theta = torch.zeros_like(table), torch.zeros_like(theta)
+        ops.field_backward_raw(product_lib, spec, table, theta, pts, None, None, g_sdf, g_nrm, None, None, None, d_table, d_theta,
+                               image=image, mode=mode)
+        out[mode] = (d_table.cpu(), d_theta.cpu())
+    for a, b, name in zip(out["tc"], out["simt"], ("d_table", "d_theta")):
+        assert float(b.abs().max()) > 0
+        assert common.rel_err(a, b) < 1e-4, (name, common.rel_err(a, b))
+        assert common.cosine(a, b) > 1 - 1e-8, (name, common.cosine(a, b))
+
+
 def test_golden_c1_render():
     gold = gc.load("c1_render.npz")
     out, grads, loss = gc.run_c1_product(gold, DEV)

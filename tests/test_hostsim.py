@@ -111,6 +111,34 @@ def test_forced_tensor_core_backward_refuses_what_it_cannot_do(hostsim_lib):
     assert common.rel_err(d_table, d_table2) < 5e-5 and common.rel_err(d_theta, d_theta2) < 5e-5
 
 
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 200])
+def test_tensor_core_backward_ragged_sizes(hostsim_lib, n):
+    """Tile edges of the tcgen05 backward kernel (64-sample tiles, two per emulated CTA sweep): a single point, one short of a
+    tile, exactly one, one over, several with a ragged tail -- forced through ls2fm_field_backward_tc, against the SIMT kernel."""
+    from levels2fm_b200 import ops
+    opt = common.make_opt("DTU", "cpu", 16, (None, 64, 64, 16), 16)
+    cfg = common.cfg_of(opt, 16)
+    sdf_sd, _ = port.random_state(cfg, seed=4, table_std=0.2)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    spec, table = sdf.field_spec(), sdf.table().detach()
+    theta = sdf.SDF_MLP.theta().detach().contiguous()
+    g = torch.Generator().manual_seed(n)
+    x = (torch.rand(n, 3, generator=g) * 1.6 - 0.8).contiguous()
+    g_sdf, g_nrm = torch.randn(n, generator=g), torch.randn(n, 3, generator=g)
+    pts = ops._points(hostsim_lib, x, None, None, None)
+    image = ops.field_prepare_raw(hostsim_lib, spec, table, theta, None)
+    out = {}
+    for mode in ("tc", "simt"):
+        d_table, d_theta = torch.zeros_like(table), torch.zeros_like(theta)
+        ops.field_backward_raw(hostsim_lib, spec, table, theta, pts, None, None, g_sdf, g_nrm, None, None, None, d_table, d_theta,
+                               image=image, mode=mode)
+        out[mode] = (d_table, d_theta)
+    for a, b, name in zip(out["tc"], out["simt"], ("d_table", "d_theta")):
+        assert float(b.abs().max()) > 0
+        assert common.rel_err(a, b) < 5e-5, (name, common.rel_err(a, b))
+
+
 def test_golden_c1_through_kernels():
     gold = gc.load("c1_render.npz")
     out, grads, loss = gc.run_c1_product(gold, "cpu")
