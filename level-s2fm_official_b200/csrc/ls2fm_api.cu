@@ -3,6 +3,7 @@
 // allocation, no global state besides a thread-local error string and the cached SM count.
 #include <stdio.h>
 
+#include <mutex>
 #include <string>
 
 #include "ls2fm_field.cuh"
@@ -48,28 +49,29 @@ static int ls_max_smem() {
     }
     return n;
 }
-// opt in to > 48 KB of dynamic shared memory, once per (kernel, device, size): the attribute call costs microseconds of host time
-// in front of every launch otherwise (one process drives one GPU, but the cache is keyed by device all the same)
-template <class K> static int ls_opt_in_smem(K kernel, int bytes) {
-    struct Entry { const void* fn; int dev; int bytes; };
-    static thread_local Entry cache[64];
-    static thread_local int n_cache = 0;
+// opt in to > 48 KB of dynamic shared memory, once per (kernel, device) and only ever upwards: the attribute call costs
+// microseconds of host time in front of every launch otherwise.  The cache is PROCESS-wide (autograd runs backward launches on its
+// own thread): the attribute is state of the function, and a second thread re-setting it to a smaller size would pull the limit
+// down under a thread that cached the larger one.
+struct LsSmemOptIn { const void* fn; int dev; int bytes; };
+static LsSmemOptIn g_optin[128];
+static int g_n_optin = 0;
+static std::mutex g_optin_mutex;
+static int ls_opt_in_smem_impl(const void* fn, int bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
-    const void* key = reinterpret_cast<const void*>(kernel);
-    for (int i = 0; i < n_cache; ++i)
-        if (cache[i].fn == key && cache[i].dev == dev) {
-            if (cache[i].bytes >= bytes) return 0;
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-            if (e != cudaSuccess) return ls_fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-            cache[i].bytes = bytes;
-            return 0;
-        }
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return ls_fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    if (n_cache < 64) cache[n_cache++] = Entry{key, dev, bytes};
+    std::lock_guard<std::mutex> lock(g_optin_mutex);
+    LsSmemOptIn* e = nullptr;
+    for (int i = 0; i < g_n_optin; ++i)
+        if (g_optin[i].fn == fn && g_optin[i].dev == dev) { e = &g_optin[i]; break; }
+    if (e && e->bytes >= bytes) return 0;
+    cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (err != cudaSuccess) return ls_fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+    if (e) e->bytes = bytes;
+    else if (g_n_optin < 128) g_optin[g_n_optin++] = LsSmemOptIn{fn, dev, bytes};
     return 0;
 }
+template <class K> static int ls_opt_in_smem(K kernel, int bytes) { return ls_opt_in_smem_impl(reinterpret_cast<const void*>(kernel), bytes); }
 static int ls_check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return ls_fail(std::string(what) + ": " + cudaGetErrorString(e));
