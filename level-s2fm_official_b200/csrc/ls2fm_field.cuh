@@ -194,11 +194,14 @@ LS_DEV void ls_stage_weights(const LsFieldArgs& a, float* smem) {
 // *out_i: where the per-sample outputs of sample i go (dense, or r * out_stride + out_offset + j for compacted rays)
 LS_DEV void ls_sample_point(const ls2fm_points_t& p, int64_t i, float x[3], int* ray_id, int64_t* out_i) {
     *out_i = i;
+    // (sample index -> ray: a 32-bit division whenever the launch has fewer than 2^31 samples -- a warp-uniform test; the 64-bit
+    //  one is a ~100-instruction subroutine that every thread of the forward kernels paid once per tile)
+    const bool small = p.n <= 0x7fffffffLL;
     if (p.xyz) {
         x[0] = __ldg(p.xyz + 3 * i); x[1] = __ldg(p.xyz + 3 * i + 1); x[2] = __ldg(p.xyz + 3 * i + 2);
-        *ray_id = p.n_per_ray > 0 ? (int)(i / p.n_per_ray) : 0;
+        *ray_id = p.n_per_ray > 0 ? (small ? (int)((uint32_t)i / (uint32_t)p.n_per_ray) : (int)(i / p.n_per_ray)) : 0;
     } else {
-        int r = (int)(i / p.n_per_ray);
+        int r = small ? (int)((uint32_t)i / (uint32_t)p.n_per_ray) : (int)(i / p.n_per_ray);
         const int j = (int)(i - (int64_t)r * p.n_per_ray);
         if (p.ray_index) r = __ldg(p.ray_index + r);
         const float t = __ldg(p.t + (int64_t)r * p.t_stride + p.t_offset + j);

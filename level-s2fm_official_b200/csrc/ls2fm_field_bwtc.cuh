@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
             }
         } else if (cg == 0) {
             if (valid && rad) {
-                const int64_t r = i / a.p.n_per_ray;
+                const int64_t r = a.p.n <= 0x7fffffffLL ? (int64_t)((uint32_t)i / (uint32_t)a.p.n_per_ray) : i / a.p.n_per_ray;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) v3[d] = __ldg(a.p.ray + 3 * r + d);
             }
