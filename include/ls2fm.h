@@ -172,6 +172,12 @@ int ls2fm_field_forward_simt(const ls2fm_field_t* field, const ls2fm_points_t* p
                              const ls2fm_radiance_t* rad,
                              float* out_y, float* out_sdf, float* out_nrm, float* out_rgb, void* stream);
 
+/* EXPERIMENTAL (round-2 groundwork; validated under the host emulator only, not yet measured on hardware, called by nothing
+ * in the package unless ops.FORWARD_WS is set): the values-only evaluation (out_y / out_sdf) by a warp-specialised kernel --
+ * four gather warps write the next tile's encoding into a shared-memory MMA operand while sixteen MLP warps run the tensor-core
+ * chain of the current one.  Same results as ls2fm_field_forward(field, pts, NULL, out_y, out_sdf, NULL, NULL). */
+int ls2fm_field_forward_ws(const ls2fm_field_t* field, const ls2fm_points_t* pts, float* out_y, float* out_sdf, void* stream);
+
 /* backward of ls2fm_field_forward.  Upstream gradients (all nullable): g_y [n,dout], g_sdf [n],
  * g_nrm [n,3], g_rgb [n,3].  saved_nrm/saved_rgb: forward outputs (required when rad != NULL).
  * Accumulates (+=, atomics) into d_table [n_entries*2], d_theta [len(theta)], d_w_eff [3*in_dim],

@@ -83,6 +83,7 @@ SIGNATURES = {
     "ls2fm_field_prepare": (C.c_int, [C.POINTER(Field), C.POINTER(Radiance), _VP, _VP]),
     "ls2fm_field_forward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_field_forward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),
+    "ls2fm_field_forward_ws": (C.c_int, [C.POINTER(Field), C.POINTER(Points), _VP, _VP, _VP]),
     "ls2fm_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),
     "ls2fm_field_backward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),
     "ls2fm_field_backward_tc": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),

@@ -9,6 +9,7 @@
 #include "ls2fm_field.cuh"
 #include "ls2fm_field_tc.cuh"
 #include "ls2fm_field_bwtc.cuh"
+#include "ls2fm_field_ws.cuh"
 #include "ls2fm_render.cuh"
 #include "ls2fm_sampler.cuh"
 #include "ls2fm_trace.cuh"
@@ -344,6 +345,27 @@ int ls2fm_field_forward(const ls2fm_field_t* field, const ls2fm_points_t* pts, c
         LS_LAUNCH(ls_field_forward_tc_kernel<false>, (unsigned)grid, LS_TC_THREADS, smem, stream, a, net, net);
     }
     return ls_check_launch("field_forward");
+}
+
+int ls2fm_field_forward_ws(const ls2fm_field_t* field, const ls2fm_points_t* pts, float* out_y, float* out_sdf, void* stream) {
+    if (ls_field_forward_checks(field, pts, nullptr, nullptr)) return 1;
+    if (pts->n == 0) return 0;
+    if (field->n_levels & 3) return ls_fail("field_forward_ws: n_levels must be a multiple of 4");
+    LsFieldArgs a;
+    ls_fill_args(a, field, pts, nullptr);
+    a.out_y = out_y; a.out_sdf = out_sdf;
+    a.net = ls_plan_net(*field, 0, 1, false);
+    const LsTcNet img = ls_plan_tc(*field, 0);
+    const LsTcNet cnet = ls_plan_tc(*field, 0, false);
+    const LsWsPlan ws = ls_plan_ws(cnet);
+    const int smem = ws.total * (int)sizeof(float);
+    if (smem > ls_max_smem()) return ls_fail("field_forward_ws: network does not fit in shared memory");
+    if (ls_opt_in_smem(ls_field_sdf_ws_kernel, smem)) return 1;
+    const int64_t n_tiles = (pts->n + LS_TC_M - 1) / LS_TC_M;
+    const int64_t n_pairs = (n_tiles + 1) / 2;
+    const int64_t grid = n_pairs < ls_sm_count() ? n_pairs : ls_sm_count();
+    LS_LAUNCH(ls_field_sdf_ws_kernel, (unsigned)grid, LS_WS_THREADS, smem, stream, a, cnet, img, ws);
+    return ls_check_launch("field_forward_ws");
 }
 
 static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,

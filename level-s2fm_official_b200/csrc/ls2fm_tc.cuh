@@ -73,6 +73,21 @@ LS_DEV void ls_tc_mma_ss(uint32_t, int d_col, const float* A, int a_lbo, const f
 LS_DEV void ls_tc_commit(LsTcBar* b) { b->arrived += 1; }
 LS_DEV void ls_tc_wait(LsTcBar*, uint32_t& phase) { __syncthreads(); phase ^= 1; }
 LS_DEV bool ls_elect() { return (threadIdx.x & 31) == 0; }
+// ---- counted mbarriers and named barriers for warp-specialised kernels (fibers yield while they spin)
+struct LsMbar { short pending; short count; int phase; };
+LS_DEV void ls_mb_init(LsMbar* b, int count) { b->pending = (short)count; b->count = (short)count; b->phase = 0; }
+LS_DEV void ls_mb_arrive(LsMbar* b) { if (--b->pending == 0) { b->pending = b->count; b->phase ^= 1; } }
+LS_DEV void ls_mb_commit(LsMbar* b) { ls_mb_arrive(b); }          // (emulated MMAs complete at issue)
+LS_DEV void ls_mb_wait(LsMbar* b, uint32_t parity) { while ((uint32_t)(b->phase & 1) == parity) simt::yield(simt::RUN); }
+struct LsNamedBarSim { int count; int gen; };
+inline LsNamedBarSim& ls_named_bar_sim(int id) { static LsNamedBarSim t[16]; return t[id]; }
+LS_DEV void ls_named_sync(int id, int nthreads) {
+    LsNamedBarSim& b = ls_named_bar_sim(id);
+    const int g = b.gen;
+    if (++b.count == nthreads) { b.count = 0; b.gen = g + 1; }
+    else while (b.gen == g) simt::yield(simt::RUN);
+}
+LS_DEV void ls_ws_sync_before_mma(int id, int nthreads) { ls_named_sync(id, nthreads); }
 LS_DEV float ls_tf32_lo(float x) { return x - ls_tf32_trunc(x); }
 LS_DEV void ls_split_tf32(float v, float& hi, float& lo) { hi = ls_tf32_round(v); lo = v - hi; }
 LS_DEV float ls_tf32_rna(float v) { return ls_tf32_round(v); }
@@ -216,6 +231,31 @@ LS_DEV void ls_split_tf32(float v, float& hi, float& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
     hi = __uint_as_float(hb);
     lo = v - hi;
+}
+// ---- counted mbarriers and named barriers for warp-specialised kernels
+struct LsMbar { unsigned long long v; };
+LS_DEV void ls_mb_init(LsMbar* b, int count) {       // one thread, then fence + barrier by the caller
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(ls_smem_u32(b)), "r"(count));
+}
+LS_DEV void ls_mb_arrive(LsMbar* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(ls_smem_u32(b)) : "memory");
+}
+LS_DEV void ls_mb_commit(LsMbar* b) {                 // one arrival once every tcgen05 op issued so far by this thread is done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(ls_smem_u32(b)) : "memory");
+}
+LS_DEV void ls_mb_wait(LsMbar* b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(ls_smem_u32(b)), "r"(parity) : "memory");
+}
+LS_DEV void ls_named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(nthreads) : "memory"); }
+// the MLP warps' version of ls_tc_sync_before_mma: a named barrier over themselves only
+LS_DEV void ls_ws_sync_before_mma(int id, int nthreads) {
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    ls_named_sync(id, nthreads);
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
 }
 LS_DEV float ls_tf32_rna(float v) {
     uint32_t hb;

@@ -217,6 +217,9 @@ def field_forward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: O
     nrm = torch.empty(n, 3, device=dev) if want_nrm else None
     rgb = torch.empty(n, 3, device=dev) if want_rgb else None
     f = spec.c_field(lib, table, theta, image)
+    if FORWARD_WS and rad is None and not want_nrm and not want_rgb and not simt:      # experimental warp-specialised kernel (tests only)
+        _call(lib, "field_forward_ws", lib.dll.ls2fm_field_forward_ws, f, pts, lib.ptr(y), lib.ptr(sdf), lib.stream())
+        return y, sdf, nrm, rgb
     _call(lib, "field_forward_simt" if simt else "field_forward", lib.dll.ls2fm_field_forward_simt if simt else lib.dll.ls2fm_field_forward, f, pts, rad, lib.ptr(y), lib.ptr(sdf), lib.ptr(nrm), lib.ptr(rgb), lib.stream())
     return y, sdf, nrm, rgb
 
@@ -297,6 +300,7 @@ def composite_backward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, 
 
 
 # ------------------------------------------------------------------------- autograd
+FORWARD_WS = False         # tests set this to route values-only evaluations through the experimental warp-specialised kernel
 BACKWARD_MODE = "auto"     # tests set "simt" / "tc" to cross-check the tensor-core backward kernel against the fp32-SIMT one
 
 def _c(t):

@@ -134,6 +134,31 @@ def test_tensor_core_backward_ragged_sizes(product_lib, n):
         assert common.cosine(a, b) > 1 - 1e-8, (name, common.cosine(a, b))
 
 
+@pytest.mark.skipif(__import__("os").environ.get("LS2FM_EXPERIMENTAL") != "1",
+                    reason="ls2fm_field_forward_ws is round-2 groundwork: emulator-validated, never run on hardware yet (set LS2FM_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("n", [1, 129, 100000])
+def test_experimental_warp_specialised_forward(product_lib, n):
+    from levels2fm_b200 import ops
+    opt = common.make_opt("DTU", DEV, 16, (None, 64, 64, 64, 16), 16)
+    cfg = common.cfg_of(opt, 16)
+    sdf_sd, _ = port.random_state(cfg, seed=6, table_std=0.2)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    spec, table = sdf.field_spec(), sdf.table().detach()
+    theta = sdf.SDF_MLP.theta().detach().contiguous()
+    x = (torch.rand(n, 3, generator=torch.Generator().manual_seed(n)) * 1.6 - 0.8).to(DEV).contiguous()
+    pts = ops._points(product_lib, x, None, None, None)
+    image = ops.field_prepare_raw(product_lib, spec, table, theta, None)
+    ref_y, ref_sdf, _, _ = ops.field_forward_raw(product_lib, spec, table, theta, pts, None, want_y=True, image=image)
+    ops.FORWARD_WS = True
+    try:
+        y, s, _, _ = ops.field_forward_raw(product_lib, spec, table, theta, pts, None, want_y=True, image=image)
+    finally:
+        ops.FORWARD_WS = False
+    torch.cuda.synchronize()
+    assert common.rel_err(y.cpu(), ref_y.cpu()) < 2e-6 and common.rel_err(s.cpu(), ref_sdf.cpu()) < 2e-6
+
+
 def test_golden_c1_render():
     gold = gc.load("c1_render.npz")
     out, grads, loss = gc.run_c1_product(gold, DEV)

@@ -139,6 +139,36 @@ def test_tensor_core_backward_ragged_sizes(hostsim_lib, n):
         assert common.rel_err(a, b) < 5e-5, (name, common.rel_err(a, b))
 
 
+@pytest.mark.parametrize("n,n_levels,layers", [(1, 16, (None, 64, 64, 64, 16)), (127, 16, (None, 64, 16)), (128, 4, (None, 64, 16)),
+                                               (129, 16, (None, 64, 64, 16)), (700, 16, (None, 64, 64, 64, 16))])
+def test_experimental_warp_specialised_forward(hostsim_lib, n, n_levels, layers):
+    """ls2fm_field_forward_ws (gather warps feeding MLP warps through a shared-memory MMA operand, counted mbarriers, named
+    barrier) against the default values-only kernel and the oracle, on tile-edge sizes.  Emulator only: the kernel is round-2
+    groundwork and has not run on hardware yet."""
+    from levels2fm_b200 import ops
+    opt = common.make_opt("DTU", "cpu", n_levels, layers, 16)
+    cfg = common.cfg_of(opt, n_levels)
+    sdf_sd, _ = port.random_state(cfg, seed=6, table_std=0.2)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    spec, table = sdf.field_spec(), sdf.table().detach()
+    theta = sdf.SDF_MLP.theta().detach().contiguous()
+    x = (torch.rand(n, 3, generator=torch.Generator().manual_seed(n)) * 1.6 - 0.8).contiguous()
+    pts = ops._points(hostsim_lib, x, None, None, None)
+    image = ops.field_prepare_raw(hostsim_lib, spec, table, theta, None)
+    ref_y, ref_sdf, _, _ = ops.field_forward_raw(hostsim_lib, spec, table, theta, pts, None, want_y=True, image=image)
+    ops.FORWARD_WS = True
+    try:
+        y, s, _, _ = ops.field_forward_raw(hostsim_lib, spec, table, theta, pts, None, want_y=True, image=image)
+        y2, s2, _, _ = ops.field_forward_raw(hostsim_lib, spec, table, theta, pts, None, want_y=True)       # no operand image
+    finally:
+        ops.FORWARD_WS = False
+    assert common.rel_err(y, ref_y) < 2e-6 and common.rel_err(s, ref_sdf) < 2e-6
+    assert common.rel_err(y2, ref_y) < 2e-6 and common.rel_err(s2, ref_sdf) < 2e-6
+    o_sdf, o_feat = port.infer_sdf(x, sdf_sd, cfg, "ret_all")
+    assert common.rel_err(s, o_sdf.reshape(-1)) < 1e-4
+
+
 def test_golden_c1_through_kernels():
     gold = gc.load("c1_render.npz")
     out, grads, loss = gc.run_c1_product(gold, "cpu")
