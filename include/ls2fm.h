@@ -172,8 +172,8 @@ int ls2fm_field_forward_simt(const ls2fm_field_t* field, const ls2fm_points_t* p
                              const ls2fm_radiance_t* rad,
                              float* out_y, float* out_sdf, float* out_nrm, float* out_rgb, void* stream);
 
-/* EXPERIMENTAL (round-2 groundwork; validated under the host emulator only, not yet measured on hardware, called by nothing
- * in the package unless ops.FORWARD_WS is set): the values-only evaluation (out_y / out_sdf) by a warp-specialised kernel --
+/* EXPERIMENTAL (round-2 groundwork; emulator-validated, one hardware run: bit-identical to the default kernel but 12 % slower
+ * with its four gather warps; called by nothing in the package unless ops.FORWARD_WS is set): the values-only evaluation (out_y / out_sdf) by a warp-specialised kernel --
  * four gather warps write the next tile's encoding into a shared-memory MMA operand while sixteen MLP warps run the tensor-core
  * chain of the current one.  Same results as ls2fm_field_forward(field, pts, NULL, out_y, out_sdf, NULL, NULL). */
 int ls2fm_field_forward_ws(const ls2fm_field_t* field, const ls2fm_points_t* pts, float* out_y, float* out_sdf, void* stream);

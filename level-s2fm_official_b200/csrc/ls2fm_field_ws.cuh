@@ -1,5 +1,7 @@
 // ls2fm_field_ws.cuh -- EXPERIMENTAL warp-specialised values-only field kernel (round-2 groundwork, opt-in through
-// ls2fm_field_forward_ws; validated against the oracle under the host emulator only -- not yet measured on a B200).
+// ls2fm_field_forward_ws).  Validated against the oracle under the host emulator; one run on a B200 at the very end of round 1
+// (tools/ws_probe.py): bit-identical to the default kernel, 185 us vs 165 us on 262 144 samples -- it works, and four gather
+// warps (16 loads in flight per thread) do not yet feed the MLP warps fast enough: next are 8-12 gather warps / deeper batching.
 //
 // Same contract as ls_field_sdf_tc_kernel (ls2fm_field_tc.cuh): hash grid -> geometry MLP -> y / sdf, nothing kept.  The field
 // kernels are bound by two things that never overlap when every warp does both: the L1 tag stage of the scattered 8-byte table

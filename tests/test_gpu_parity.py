@@ -135,7 +135,7 @@ def test_tensor_core_backward_ragged_sizes(product_lib, n):
 
 
 @pytest.mark.skipif(__import__("os").environ.get("LS2FM_EXPERIMENTAL") != "1",
-                    reason="ls2fm_field_forward_ws is round-2 groundwork: emulator-validated, never run on hardware yet (set LS2FM_EXPERIMENTAL=1)")
+                    reason="ls2fm_field_forward_ws is round-2 groundwork, not part of the product path (set LS2FM_EXPERIMENTAL=1 to run it)")
 @pytest.mark.parametrize("n", [1, 129, 100000])
 def test_experimental_warp_specialised_forward(product_lib, n):
     from levels2fm_b200 import ops
