@@ -2,6 +2,7 @@
 // Built by nvcc for sm_100a (see level-s2fm_official_b200/build.py).  No host synchronisation, no device
 // allocation, no global state besides a thread-local error string and the cached SM count.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <string>
@@ -360,11 +361,17 @@ int ls2fm_field_forward_ws(const ls2fm_field_t* field, const ls2fm_points_t* pts
     const LsWsPlan ws = ls_plan_ws(cnet);
     const int smem = ws.total * (int)sizeof(float);
     if (smem > ls_max_smem()) return ls_fail("field_forward_ws: network does not fit in shared memory");
-    if (ls_opt_in_smem(ls_field_sdf_ws_kernel, smem)) return 1;
     const int64_t n_tiles = (pts->n + LS_TC_M - 1) / LS_TC_M;
     const int64_t n_pairs = (n_tiles + 1) / 2;
     const int64_t grid = n_pairs < ls_sm_count() ? n_pairs : ls_sm_count();
-    LS_LAUNCH(ls_field_sdf_ws_kernel, (unsigned)grid, LS_WS_THREADS, smem, stream, a, cnet, img, ws);
+    const char* gw = getenv("LS2FM_WS_GATHER_WARPS");        // experiment knob: 4 (default) or 8
+    if (gw && atoi(gw) == 8) {
+        if (ls_opt_in_smem(ls_field_sdf_ws_kernel<8>, smem)) return 1;
+        LS_LAUNCH(ls_field_sdf_ws_kernel<8>, (unsigned)grid, ls_ws_threads(8), smem, stream, a, cnet, img, ws);
+    } else {
+        if (ls_opt_in_smem(ls_field_sdf_ws_kernel<4>, smem)) return 1;
+        LS_LAUNCH(ls_field_sdf_ws_kernel<4>, (unsigned)grid, ls_ws_threads(4), smem, stream, a, cnet, img, ws);
+    }
     return ls_check_launch("field_forward_ws");
 }
 

@@ -18,8 +18,8 @@
 
 #include "ls2fm_field_tc.cuh"
 
-constexpr int LS_WS_GW = 4;                                     // gather warps
-constexpr int LS_WS_THREADS = LS_TC_THREADS + 32 * LS_WS_GW;    // 640
+// GW gather warps: 4 (one thread per sample, all levels) or 8 (two threads per sample, half of the levels each)
+constexpr int ls_ws_threads(int gw) { return LS_TC_THREADS + 32 * gw; }
 
 struct LsWsPlan {
     int eb;         // [2 buffers][hi | lo][128 x k_in_pad0] A operand of layer 0:  addr(m, k) = (k / 4) * 512 + m * 4 + k % 4
@@ -37,8 +37,10 @@ inline LsWsPlan ls_plan_ws(const LsTcNet& cnet) {
     return w;
 }
 
-__global__ void __launch_bounds__(LS_WS_THREADS, 1) ls_field_sdf_ws_kernel(const LsFieldArgs a, const LsTcNet net, const LsTcNet img,
-                                                                           const LsWsPlan ws) {
+template <int GW>
+__global__ void __launch_bounds__(ls_ws_threads(GW), 1) ls_field_sdf_ws_kernel(const LsFieldArgs a, const LsTcNet net, const LsTcNet img,
+                                                                               const LsWsPlan ws) {
+    static_assert(GW == 4 || GW == 8, "4 or 8 gather warps");
     LS_DYN_SMEM(smem);
     if (ls_n_samples(a.p) == 0) return;
     const int t = threadIdx.x, warp = t >> 5;
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(LS_WS_THREADS, 1) ls_field_sdf_ws_kernel(const
     const uint32_t tmem = ls_tc_alloc(slot);
     if (t == 0) {
         ls_mb_init(bar0, 1); ls_mb_init(bar1, 1);
-        ls_mb_init(full + 0, 32 * LS_WS_GW); ls_mb_init(full + 1, 32 * LS_WS_GW);
+        ls_mb_init(full + 0, 32 * GW); ls_mb_init(full + 1, 32 * GW);
         ls_mb_init(empty + 0, 1 + LS_TC_THREADS); ls_mb_init(empty + 1, 1 + LS_TC_THREADS);
 #if !defined(LS_HOSTSIM)
         asm volatile("fence.mbarrier_init.release.cluster;\n");
@@ -84,7 +86,9 @@ __global__ void __launch_bounds__(LS_WS_THREADS, 1) ls_field_sdf_ws_kernel(const
 
     if (is_gather) {
         // ================================================================ gather warps: one sample per thread, one tile ahead
-        const int g = t - LS_TC_THREADS;
+        const int g = (t - LS_TC_THREADS) & (LS_TC_M - 1);         // sample row
+        const int part = (t - LS_TC_THREADS) / LS_TC_M;            // which share of the levels (GW == 8: two threads per sample)
+        const int l_per = L / (GW / 4), l_begin = part * l_per, l_end = l_begin + l_per;     // (L % 4 == 0: both shares are even)
         for (int64_t n = 0; n < my_tiles; ++n) {
             const int b = (int)(n & 1);
             ls_mb_wait(empty + b, (uint32_t)(((n >> 1) & 1) ^ 1));      // (first use of a buffer: passes at once)
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(LS_WS_THREADS, 1) ls_field_sdf_ws_kernel(const
             ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
             float* Eh = EB + b * ebuf;
             float* El = Eh + LS_TC_M * Kp0;
-            for (int l = 0; l < L; l += 2) {        // two levels = four consecutive K columns = one 16-byte store per array
+            for (int l = l_begin; l < l_end; l += 2) {      // two levels = four consecutive K columns = one 16-byte store per array
                 float h0[2], h1[2], dh[2][3];
                 ls_level_eval(a.f, l, u, h0, dh);
                 ls_level_eval(a.f, l + 1, u, h1, dh);
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(LS_WS_THREADS, 1) ls_field_sdf_ws_kernel(const
                 ls_st4(Eh + o, make_float4(hi[0], hi[1], hi[2], hi[3]));
                 ls_st4(El + o, make_float4(lo[0], lo[1], lo[2], lo[3]));
             }
-            {   // tail: x / rescale, the ones column (bias of layer 0), zero padding
+            if (part == 0) {    // tail: x / rescale, the ones column (bias of layer 0), zero padding; the sample's output index
                 float hi[4], lo[4];
                 for (int d = 0; d < 3; ++d) ls_split_tf32(ls_fdiv(x[d], a.f.rescale), hi[d], lo[d]);
                 hi[3] = 1.f; lo[3] = 0.f;
@@ -121,8 +125,8 @@ __global__ void __launch_bounds__(LS_WS_THREADS, 1) ls_field_sdf_ws_kernel(const
                     ls_st4(Eh + oz, make_float4(0.f, 0.f, 0.f, 0.f));
                     ls_st4(El + oz, make_float4(0.f, 0.f, 0.f, 0.f));
                 }
+                OI[b * LS_TC_M + g] = valid ? (long long)io : -1;
             }
-            OI[b * LS_TC_M + g] = valid ? (long long)io : -1;
             ls_fence_smem_to_async();
             ls_mb_arrive(full + b);
         }

@@ -1,5 +1,8 @@
 """GPU diagnostic for the experimental warp-specialised values-only kernel: parity against the default kernel and device time on
-the sampler's first launch shape (4096 rays x 64 uniform samples, C2 SDF network).  python tools/ws_probe.py"""
+the sampler's first launch shape (4096 rays x 64 uniform samples, C2 SDF network).
+    python tools/ws_probe.py                              (4 gather warps)
+    LS2FM_WS_GATHER_WARPS=8 python tools/ws_probe.py      (8 gather warps: two threads per sample)
+Round 1, B200, 4 gather warps: bit-identical, 185 us vs 165 us for the default kernel."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import port
