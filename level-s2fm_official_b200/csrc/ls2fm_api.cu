@@ -364,14 +364,18 @@ int ls2fm_field_forward_ws(const ls2fm_field_t* field, const ls2fm_points_t* pts
     const int64_t n_tiles = (pts->n + LS_TC_M - 1) / LS_TC_M;
     const int64_t n_pairs = (n_tiles + 1) / 2;
     const int64_t grid = n_pairs < ls_sm_count() ? n_pairs : ls_sm_count();
-    const char* gw = getenv("LS2FM_WS_GATHER_WARPS");        // experiment knob: 4 (default) or 8
-    if (gw && atoi(gw) == 8) {
-        if (ls_opt_in_smem(ls_field_sdf_ws_kernel<8>, smem)) return 1;
-        LS_LAUNCH(ls_field_sdf_ws_kernel<8>, (unsigned)grid, ls_ws_threads(8), smem, stream, a, cnet, img, ws);
-    } else {
-        if (ls_opt_in_smem(ls_field_sdf_ws_kernel<4>, smem)) return 1;
-        LS_LAUNCH(ls_field_sdf_ws_kernel<4>, (unsigned)grid, ls_ws_threads(4), smem, stream, a, cnet, img, ws);
-    }
+    // experiment knobs: LS2FM_WS_GATHER_WARPS = 4 (default) | 8, LS2FM_WS_DEPTH = 2 (default) | 4 levels per load batch
+    const char* gw = getenv("LS2FM_WS_GATHER_WARPS");
+    const char* dp = getenv("LS2FM_WS_DEPTH");
+    const bool gw8 = gw && atoi(gw) == 8, dp4 = dp && atoi(dp) == 4 && (field->n_levels / (gw8 ? 2 : 1)) % 4 == 0;
+#define LS_WS_LAUNCH(GWV, DPV)                                                                                          \
+    do {                                                                                                                \
+        if (ls_opt_in_smem(ls_field_sdf_ws_kernel<GWV, DPV>, smem)) return 1;                                           \
+        LS_LAUNCH((ls_field_sdf_ws_kernel<GWV, DPV>), (unsigned)grid, ls_ws_threads(GWV), smem, stream, a, cnet, img, ws); \
+    } while (0)
+    if (gw8) { if (dp4) LS_WS_LAUNCH(8, 4); else LS_WS_LAUNCH(8, 2); }
+    else { if (dp4) LS_WS_LAUNCH(4, 4); else LS_WS_LAUNCH(4, 2); }
+#undef LS_WS_LAUNCH
     return ls_check_launch("field_forward_ws");
 }
 

@@ -37,10 +37,12 @@ inline LsWsPlan ls_plan_ws(const LsTcNet& cnet) {
     return w;
 }
 
-template <int GW>
+// DEPTH: levels evaluated back to back before their results are stored (2 or 4): 16 or 32 table reads in flight per gather thread
+template <int GW, int DEPTH>
 __global__ void __launch_bounds__(ls_ws_threads(GW), 1) ls_field_sdf_ws_kernel(const LsFieldArgs a, const LsTcNet net, const LsTcNet img,
                                                                                const LsWsPlan ws) {
     static_assert(GW == 4 || GW == 8, "4 or 8 gather warps");
+    static_assert(DEPTH == 2 || DEPTH == 4, "2 or 4 levels per batch");
     LS_DYN_SMEM(smem);
     if (ls_n_samples(a.p) == 0) return;
     const int t = threadIdx.x, warp = t >> 5;
@@ -102,16 +104,19 @@ __global__ void __launch_bounds__(ls_ws_threads(GW), 1) ls_field_sdf_ws_kernel(c
             ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
             float* Eh = EB + b * ebuf;
             float* El = Eh + LS_TC_M * Kp0;
-            for (int l = l_begin; l < l_end; l += 2) {      // two levels = four consecutive K columns = one 16-byte store per array
-                float h0[2], h1[2], dh[2][3];
-                ls_level_eval(a.f, l, u, h0, dh);
-                ls_level_eval(a.f, l + 1, u, h1, dh);
-                float hi[4], lo[4];
-                ls_split_tf32(h0[0], hi[0], lo[0]); ls_split_tf32(h0[1], hi[1], lo[1]);
-                ls_split_tf32(h1[0], hi[2], lo[2]); ls_split_tf32(h1[1], hi[3], lo[3]);
-                const int o = ((2 * l) >> 2) * (4 * LS_TC_M) + g * 4;
-                ls_st4(Eh + o, make_float4(hi[0], hi[1], hi[2], hi[3]));
-                ls_st4(El + o, make_float4(lo[0], lo[1], lo[2], lo[3]));
+            for (int l = l_begin; l < l_end; l += DEPTH) {  // two levels = four consecutive K columns = one 16-byte store per array
+                float h[DEPTH][2], dh[2][3];
+#pragma unroll
+                for (int j = 0; j < DEPTH; ++j) ls_level_eval(a.f, l + j, u, h[j], dh);      // (all loads of the batch issue first)
+#pragma unroll
+                for (int j = 0; j < DEPTH; j += 2) {
+                    float hi[4], lo[4];
+                    ls_split_tf32(h[j][0], hi[0], lo[0]); ls_split_tf32(h[j][1], hi[1], lo[1]);
+                    ls_split_tf32(h[j + 1][0], hi[2], lo[2]); ls_split_tf32(h[j + 1][1], hi[3], lo[3]);
+                    const int o = ((2 * (l + j)) >> 2) * (4 * LS_TC_M) + g * 4;
+                    ls_st4(Eh + o, make_float4(hi[0], hi[1], hi[2], hi[3]));
+                    ls_st4(El + o, make_float4(lo[0], lo[1], lo[2], lo[3]));
+                }
             }
             if (part == 0) {    // tail: x / rescale, the ones column (bias of layer 0), zero padding; the sample's output index
                 float hi[4], lo[4];

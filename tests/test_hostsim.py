@@ -139,15 +139,16 @@ def test_tensor_core_backward_ragged_sizes(hostsim_lib, n):
         assert common.rel_err(a, b) < 5e-5, (name, common.rel_err(a, b))
 
 
-@pytest.mark.parametrize("gather_warps", [4, 8])
+@pytest.mark.parametrize("gather_warps,depth", [(4, 2), (8, 2), (4, 4), (8, 4)])
 @pytest.mark.parametrize("n,n_levels,layers", [(1, 16, (None, 64, 64, 64, 16)), (127, 16, (None, 64, 16)), (128, 4, (None, 64, 16)),
                                                (129, 16, (None, 64, 64, 16)), (700, 16, (None, 64, 64, 64, 16))])
-def test_experimental_warp_specialised_forward(hostsim_lib, monkeypatch, n, n_levels, layers, gather_warps):
+def test_experimental_warp_specialised_forward(hostsim_lib, monkeypatch, n, n_levels, layers, gather_warps, depth):
     """ls2fm_field_forward_ws (gather warps feeding MLP warps through a shared-memory MMA operand, counted mbarriers, named
     barrier) against the default values-only kernel and the oracle, on tile-edge sizes.  Emulator only: the kernel is round-2
     groundwork (one hardware run so far: bit-identical, not yet faster).  gather_warps: one or two threads per sample."""
     from levels2fm_b200 import ops
     monkeypatch.setenv("LS2FM_WS_GATHER_WARPS", str(gather_warps))
+    monkeypatch.setenv("LS2FM_WS_DEPTH", str(depth))
     opt = common.make_opt("DTU", "cpu", n_levels, layers, 16)
     cfg = common.cfg_of(opt, n_levels)
     sdf_sd, _ = port.random_state(cfg, seed=6, table_std=0.2)

@@ -2,6 +2,7 @@
 the sampler's first launch shape (4096 rays x 64 uniform samples, C2 SDF network).
     python tools/ws_probe.py                              (4 gather warps)
     LS2FM_WS_GATHER_WARPS=8 python tools/ws_probe.py      (8 gather warps: two threads per sample)
+    LS2FM_WS_DEPTH=4 python tools/ws_probe.py             (4 levels = 32 table reads in flight per gather thread)
 Round 1, B200, 4 gather warps: bit-identical, 185 us vs 165 us for the default kernel."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
