@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LS2FM_ABI_VERSION 1
+#define LS2FM_ABI_VERSION 2
 #define LS2FM_MAX_LEVELS 16
 #define LS2FM_MAX_LAYERS 4   /* linear layers of the geometry MLP: 1..3 hidden (width 64) + output */
 #define LS2FM_HIDDEN 64
@@ -178,19 +178,36 @@ int ls2fm_field_forward_simt(const ls2fm_field_t* field, const ls2fm_points_t* p
  * chain of the current one.  Same results as ls2fm_field_forward(field, pts, NULL, out_y, out_sdf, NULL, NULL). */
 int ls2fm_field_forward_ws(const ls2fm_field_t* field, const ls2fm_points_t* pts, float* out_y, float* out_sdf, void* stream);
 
+/* Gradients w.r.t. the sample POSITIONS (all nullable; pass NULL for the whole struct when none is wanted).  tiny-cuda-nn
+ * propagates input gradients and the reference consumes them: SDF.gradient (models/SDF.py:102-114, create_graph=True) is
+ * differentiated again w.r.t. p, and BA feeds get_surface_pts' output back into infer_sdf (pipelines/BA.py:123-125), so
+ * d loss / d x flows into the first evaluation's normals.  With the upstream gradients of ls2fm_field_backward,
+ *   dL/dx = Je^T ebar  +  (d(Je nbar)/dx)^T ebar_dot  +  W_eff[:,0:3]^T pbar
+ * (Je = d enc / dx; ebar / ebar_dot the adjoints of the encoding in the primal / tangent channel; the middle term is the
+ * hash grid's mixed second derivative; the last one the radiance decoder's direct dependence on x).
+ *   explicit mode: d_xyz [n,3] is WRITTEN.
+ *   ray mode (x = center + ray * t): d_center [n_rays,3] += sum_j dL/dx,  d_ray [n_rays,3] += sum_j t_j dL/dx + the gradient
+ *   through the Fourier embedding of the direction (radiance),  d_t [n_rays, n_per_ray] is WRITTEN (= ray . dL/dx).
+ *   d_ray also accepts explicit points that carry rays (pts.xyz and pts.ray set): only the Fourier term then. */
+typedef struct {
+    float* d_xyz;
+    float* d_center;
+    float* d_ray;
+    float* d_t;
+} ls2fm_input_grads_t;
+
 /* backward of ls2fm_field_forward.  Upstream gradients (all nullable): g_y [n,dout], g_sdf [n],
  * g_nrm [n,3], g_rgb [n,3].  saved_nrm/saved_rgb: forward outputs (required when rad != NULL).
  * Accumulates (+=, atomics) into d_table [n_entries*2], d_theta [len(theta)], d_w_eff [3*in_dim],
  * d_b_eff [3]; writes d_geo2 [n,k_geo2+1]; each nullable.  The second-order path (gradient of the
- * normals w.r.t. the parameters, SDF.gradient's create_graph=True) is included.  Gradients w.r.t. the
- * sample positions are not produced: in the reference the only consumers of such a gradient sit behind
- * vren's RayAABBIntersector, which defines no backward (utils/custom_functions.py:10-31). */
+ * normals w.r.t. the parameters, SDF.gradient's create_graph=True) is included.  in_grads (nullable): gradients
+ * w.r.t. the sample positions, see ls2fm_input_grads_t. */
 int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts,
                          const ls2fm_radiance_t* rad,
                          const float* g_y, const float* g_sdf, const float* g_nrm, const float* g_rgb,
                          const float* saved_nrm, const float* saved_rgb,
                          float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
-                         void* stream);
+                         const ls2fm_input_grads_t* in_grads, void* stream);
 /* ls2fm_field_backward dispatches: launches of >= 8192 samples whose normals carry gradient (field.tc_image set,
  * n_levels % 4 == 0) run the tcgen05 kernel -- every matrix product of the 2-channel forward / reverse pass and every weight
  * gradient as 3xTF32 tensor-core batches (fp32-level), weights streamed from the operand image, weight gradients accumulated in
@@ -201,13 +218,13 @@ int ls2fm_field_backward_simt(const ls2fm_field_t* field, const ls2fm_points_t* 
                               const float* g_y, const float* g_sdf, const float* g_nrm, const float* g_rgb,
                               const float* saved_nrm, const float* saved_rgb,
                               float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
-                              void* stream);
+                              const ls2fm_input_grads_t* in_grads, void* stream);
 int ls2fm_field_backward_tc(const ls2fm_field_t* field, const ls2fm_points_t* pts,
                             const ls2fm_radiance_t* rad,
                             const float* g_y, const float* g_sdf, const float* g_nrm, const float* g_rgb,
                             const float* saved_nrm, const float* saved_rgb,
                             float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
-                            void* stream);
+                            const ls2fm_input_grads_t* in_grads, void* stream);
 
 /* ------------------------------------------------------------------ compositing
  * replaces SDF.sdf_to_sigma + Renderer.composite + the background tail of Renderer.forward
@@ -219,13 +236,14 @@ int ls2fm_composite_forward(const float* ray, const float* t, const float* sdf, 
                             const float bgcolor[3], int32_t n_rays, int32_t n_samples,
                             float* rgb, float* depth, float* normal, float* opacity, void* stream);
 /* upstream g_rgb [R,3], g_depth [R], g_normal [R,3] (nullable each) ->
- * d_sdf [R,N], d_rgbs [R,N,3], d_nrm [R,N,3] (written), d_beta_param (+=, scalar), d_ray [R,3] (+=, nullable) */
+ * d_sdf [R,N], d_rgbs [R,N,3], d_nrm [R,N,3] (written), d_beta_param (+=, scalar), d_ray [R,3] (+=, nullable: through the
+ * interval lengths |ray| (t_{i+1} - t_i)), d_t [R,N] (written, nullable: depths enter the depth output and the intervals) */
 int ls2fm_composite_backward(const float* ray, const float* t, const float* sdf, const float* rgbs,
                              const float* nrm, const float* beta_param, float beta_speed,
                              const float bgcolor[3], int32_t n_rays, int32_t n_samples,
                              const float* g_rgb, const float* g_depth, const float* g_normal,
                              float* d_sdf, float* d_rgbs, float* d_nrm, float* d_beta_param, float* d_ray,
-                             void* stream);
+                             float* d_t, void* stream);
 
 /* ------------------------------------------------------------------ depth samplers
  * Renderer.sample_depth after the AABB test (models/Renderer.py:118-127,178-185):

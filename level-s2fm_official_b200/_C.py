@@ -21,7 +21,7 @@ MAX_LAYERS = 4
 HIDDEN = 64
 MAX_OUT = 20
 MAX_RAD_IN = 68
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Level(C.Structure):
@@ -64,6 +64,10 @@ class Radiance(C.Structure):
                 ("k_geo", C.c_int32), ("k_geo2", C.c_int32), ("geo2", C.c_void_p)]
 
 
+class InputGrads(C.Structure):
+    _fields_ = [("d_xyz", C.c_void_p), ("d_center", C.c_void_p), ("d_ray", C.c_void_p), ("d_t", C.c_void_p)]
+
+
 _F3 = C.c_float * 3
 _VP = C.c_void_p
 
@@ -84,11 +88,11 @@ SIGNATURES = {
     "ls2fm_field_forward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_field_forward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_field_forward_ws": (C.c_int, [C.POINTER(Field), C.POINTER(Points), _VP, _VP, _VP]),
-    "ls2fm_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),
-    "ls2fm_field_backward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),
-    "ls2fm_field_backward_tc": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 12),
+    "ls2fm_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 11 + [C.POINTER(InputGrads), _VP]),
+    "ls2fm_field_backward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 11 + [C.POINTER(InputGrads), _VP]),
+    "ls2fm_field_backward_tc": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 11 + [C.POINTER(InputGrads), _VP]),
     "ls2fm_composite_forward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 5),
-    "ls2fm_composite_backward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 9),
+    "ls2fm_composite_backward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 10),
     "ls2fm_sample_uniform": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _F3, _F3, _VP, _VP, _VP]),
     "ls2fm_sampler_workspace_bytes": (C.c_int64, [C.POINTER(SamplerCfg), C.c_int32]),
     "ls2fm_render_loss": (C.c_int, [_VP, _VP, C.c_int64, _VP, C.c_int64, C.c_float, C.c_float, _VP, _VP, _VP, _VP]),

@@ -66,6 +66,7 @@ def default_opt(dataset: str = "DTU", device: str = "cuda", **overrides) -> Attr
                         sdf_threshold=1e-3, max_bisection_itr=10),
             Hash_config=dict(config_file=DEFAULT_HASH_CONFIG)),
         RadF=dict(arch=dict(layers=[None, 64, 64, 3], skip=[])),
+        Renderer=dict(rand_rays=8192),      # options/LevelS2fM.yaml:133-134; aabb_grad (ours, default on): see Renderer.volsdf_sampling
         data=dict(dataset=dataset, inside=ds["inside"], bg_sdf=False, bg_rad=2,
                   image_size=ds["image_size"], bound_max=[b, b, b], bound_min=[-b, -b, -b], bgcolor=ds["bgcolor"]),
     )

@@ -382,7 +382,7 @@ int ls2fm_field_forward_ws(const ls2fm_field_t* field, const ls2fm_points_t* pts
 static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
                                   const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
                                   const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
-                                  void* stream, int mode /* 0 auto, 1 simt, 2 tensor core or fail */) {
+                                  const ls2fm_input_grads_t* in_grads, void* stream, int mode /* 0 auto, 1 simt, 2 tensor core or fail */) {
     if (ls_check_field(field) || ls_check_points(pts)) return 1;
     if (pts->n == 0) return 0;
     if (rad && ls_check_rad(rad, field, pts)) return 1;
@@ -394,14 +394,19 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
     a.g_y = g_y; a.g_sdf = g_sdf; a.g_nrm = g_nrm; a.g_rgb = g_rgb;
     a.saved_nrm = saved_nrm; a.saved_rgb = saved_rgb;
     a.d_table = d_table; a.d_theta = d_theta; a.d_w_eff = d_w_eff; a.d_b_eff = d_b_eff; a.d_geo2 = d_geo2;
+    if (in_grads) a.ig = *in_grads;
+    const bool want_dx = a.ig.d_xyz || a.ig.d_center || a.ig.d_ray || a.ig.d_t;
+    if (pts->xyz && (a.ig.d_center || a.ig.d_t)) return ls_fail("field_backward: d_center / d_t need ray mode (points.xyz == NULL)");
+    if (!pts->xyz && a.ig.d_xyz) return ls_fail("field_backward: d_xyz needs explicit points; ray mode yields d_center / d_ray / d_t");
+    if (a.ig.d_ray && !pts->ray) return ls_fail("field_backward: d_ray needs points.ray");
     const bool with_rad = rad && g_rgb;
     const bool tan = with_rad || g_nrm;
     const int KL = field->n_layers;
     // ---- tensor-core kernel: needs the operand image (weights stream from it), the 2-channel form (normals carry gradient),
     //      chunk-aligned level groups and matrices that fit a ring slot; everything else runs the fp32-SIMT kernel below
     //      Launches below LS_BT_MIN_SAMPLES stay on the SIMT kernel: a few tiles do not amortise the tensor-core kernel's set-up.
-    const bool tc_ok = tan && field->tc_image && (field->n_levels & 3) == 0;
-    if (mode == 2 && !tc_ok) return ls_fail("field_backward_tc: needs field.tc_image, a gradient on the normals and n_levels % 4 == 0");
+    const bool tc_ok = tan && field->tc_image && (field->n_levels & 3) == 0 && !want_dx;
+    if (mode == 2 && !tc_ok) return ls_fail("field_backward_tc: needs field.tc_image, a gradient on the normals, n_levels % 4 == 0 and no position gradients");
     if ((mode == 2 || (mode == 0 && pts->n >= LS_BT_MIN_SAMPLES)) && tc_ok) {
         const LsTcNet img = ls_plan_tc(*field, with_rad ? rad->in_dim : 0);
         const LsBtNet net = ls_plan_bt(*field, with_rad ? rad->in_dim : 0);
@@ -443,25 +448,25 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
 int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
                          const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
                          const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
-                         void* stream) {
+                         const ls2fm_input_grads_t* in_grads, void* stream) {
     return ls_field_backward_impl(field, pts, rad, g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb, d_table, d_theta, d_w_eff, d_b_eff,
-                                  d_geo2, stream, 0);
+                                  d_geo2, in_grads, stream, 0);
 }
 
 int ls2fm_field_backward_simt(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
                               const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
                               const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
-                              void* stream) {
+                              const ls2fm_input_grads_t* in_grads, void* stream) {
     return ls_field_backward_impl(field, pts, rad, g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb, d_table, d_theta, d_w_eff, d_b_eff,
-                                  d_geo2, stream, 1);
+                                  d_geo2, in_grads, stream, 1);
 }
 
 int ls2fm_field_backward_tc(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
                             const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,
                             const float* saved_rgb, float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
-                            void* stream) {
+                            const ls2fm_input_grads_t* in_grads, void* stream) {
     return ls_field_backward_impl(field, pts, rad, g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb, d_table, d_theta, d_w_eff, d_b_eff,
-                                  d_geo2, stream, 2);
+                                  d_geo2, in_grads, stream, 2);
 }
 
 int ls2fm_composite_forward(const float* ray, const float* t, const float* sdf, const float* rgbs, const float* nrm,
@@ -479,7 +484,7 @@ int ls2fm_composite_forward(const float* ray, const float* t, const float* sdf, 
 int ls2fm_composite_backward(const float* ray, const float* t, const float* sdf, const float* rgbs, const float* nrm,
                              const float* beta_param, float beta_speed, const float bgcolor[3], int32_t n_rays, int32_t n_samples,
                              const float* g_rgb, const float* g_depth, const float* g_normal, float* d_sdf, float* d_rgbs,
-                             float* d_nrm, float* d_beta_param, float* d_ray, void* stream) {
+                             float* d_nrm, float* d_beta_param, float* d_ray, float* d_t, void* stream) {
     if (n_rays < 0 || n_samples < 2) return ls_fail("composite_backward: need n_samples >= 2");
     if (n_samples - 1 > 32 * LS_MAX_CHUNKS) return ls_fail("composite_backward: at most 257 samples per ray");
     if (n_rays > 0 && (!ray || !t || !sdf || !beta_param)) return ls_fail("composite_backward: NULL input");
@@ -487,7 +492,7 @@ int ls2fm_composite_backward(const float* ray, const float* t, const float* sdf,
     const int wpb = 4;
     LS_LAUNCH(ls_composite_backward_kernel, (unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, 0, stream, ray, t, sdf, rgbs, nrm,
               beta_param, beta_speed, bgcolor[0], bgcolor[1], bgcolor[2], n_rays, n_samples, g_rgb, g_depth, g_normal, d_sdf,
-              d_rgbs, d_nrm, d_beta_param, d_ray);
+              d_rgbs, d_nrm, d_beta_param, d_ray, d_t);
     return ls_check_launch("composite_backward");
 }
 

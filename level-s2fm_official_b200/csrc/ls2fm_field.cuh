@@ -56,6 +56,7 @@ struct LsFieldArgs {
     const float* g_y; const float* g_sdf; const float* g_nrm; const float* g_rgb;
     const float* saved_nrm; const float* saved_rgb;
     float* d_table; float* d_theta; float* d_w_eff; float* d_b_eff; float* d_geo2;
+    ls2fm_input_grads_t ig;   // gradients w.r.t. the sample positions (all NULL: not wanted)
 };
 
 inline int ls_round4(int v) { return (v + 3) & ~3; }
@@ -899,8 +900,13 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
             __syncthreads();
         }
 
-        // ------------------------------------------------ B6: hash-table gradient scatter
-        if (a.d_table && valid) {
+        // ------------------------------------------------ B6: hash-table gradient scatter (+ gradient w.r.t. the sample position)
+        // dL/dx = Je^T ebar + (d(Je nbar)/dx)^T ebar_dot (+ radiance's direct x term): the table values are gathered once more and
+        // contracted with the first / mixed second derivatives of the trilinear weights (diagonal second derivatives
+        // of a trilinear cell are zero).  P rows = ebar, Pd rows = ebar_dot (left there by layer 0's reverse step).
+        const bool want_dx = a.ig.d_xyz || a.ig.d_center || a.ig.d_ray || a.ig.d_t;
+        float dx[3] = {0.f, 0.f, 0.f};
+        if ((a.d_table || want_dx) && valid) {
 #pragma unroll 1
             for (int r = 0; r < 4; ++r) {
                 const int l = g + 4 * r;
@@ -918,19 +924,96 @@ __global__ void __launch_bounds__(LS_BW_THREADS, 1) ls_field_backward_kernel(con
 #pragma unroll
                         for (int d = 0; d < 3; ++d) ns[d] = nbar[d] * scale * a.inv_ext[d];
                     }
+                    if (a.d_table) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float f0 = (k & 1) ? c.w[0] : 1.f - c.w[0];
-                        const float f1 = (k & 2) ? c.w[1] : 1.f - c.w[1];
-                        const float f2 = (k & 4) ? c.w[2] : 1.f - c.w[2];
-                        const float wgt = f0 * f1 * f2;
-                        float g0 = wgt * e0, g1 = wgt * e1;
-                        if (TAN) {
-                            const float dw = ((k & 1) ? ns[0] : -ns[0]) * f1 * f2 + ((k & 2) ? ns[1] : -ns[1]) * f0 * f2 +
-                                             ((k & 4) ? ns[2] : -ns[2]) * f0 * f1;
-                            g0 += dw * t0; g1 += dw * t1;
+                        for (int k = 0; k < 8; ++k) {
+                            const float f0 = (k & 1) ? c.w[0] : 1.f - c.w[0];
+                            const float f1 = (k & 2) ? c.w[1] : 1.f - c.w[1];
+                            const float f2 = (k & 4) ? c.w[2] : 1.f - c.w[2];
+                            const float wgt = f0 * f1 * f2;
+                            float g0 = wgt * e0, g1 = wgt * e1;
+                            if (TAN) {
+                                const float dw = ((k & 1) ? ns[0] : -ns[0]) * f1 * f2 + ((k & 2) ? ns[1] : -ns[1]) * f0 * f2 +
+                                                 ((k & 4) ? ns[2] : -ns[2]) * f0 * f1;
+                                g0 += dw * t0; g1 += dw * t1;
+                            }
+                            atomicAdd(reinterpret_cast<float2*>(tab) + ci[k], make_float2(g0, g1));
                         }
-                        atomicAdd(reinterpret_cast<float2*>(tab) + ci[k], make_float2(g0, g1));
+                    }
+                    if (want_dx) {
+                        const float2* vt = reinterpret_cast<const float2*>(a.f.table + 2 * (size_t)a.f.levels[l].offset);
+                        float lx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float2 v = __ldg(vt + ci[k]);
+                            const float fk[3] = {(k & 1) ? c.w[0] : 1.f - c.w[0], (k & 2) ? c.w[1] : 1.f - c.w[1], (k & 4) ? c.w[2] : 1.f - c.w[2]};
+                            const float sg3[3] = {(k & 1) ? 1.f : -1.f, (k & 2) ? 1.f : -1.f, (k & 4) ? 1.f : -1.f};
+                            const float Ak = v.x * e0 + v.y * e1;
+                            const float Bk = TAN ? v.x * t0 + v.y * t1 : 0.f;
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+                                float term = fk[d1] * fk[d2] * Ak;
+                                if (TAN) term += (sg3[d1] * ns[d1] * fk[d2] + sg3[d2] * ns[d2] * fk[d1]) * Bk;
+                                lx[d] += sg3[d] * term;
+                            }
+                        }
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) dx[d] += lx[d] * scale * a.inv_ext[d];
+                    }
+                }
+            }
+        }
+        if (want_dx) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                dx[d] += __shfl_xor_sync(0xffffffffu, dx[d], 8);
+                dx[d] += __shfl_xor_sync(0xffffffffu, dx[d], 16);
+            }
+            if (g == 0 && valid) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    dx[d] += ls_el(P, LS_H, d, s8) / a.f.rescale;
+                    if (rad) dx[d] += Weff[d] * pbar[0] + Weff[RP + d] * pbar[1] + Weff[2 * RP + d] * pbar[2];
+                }
+                float dirg[3] = {0.f, 0.f, 0.f};     // gradient through the Fourier embedding of the direction
+                if (rad && a.ig.d_ray) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const float dv = __ldg(a.p.ray + 3 * ray_id + d);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float acc = Weff[c * RP + o_ray + d];
+                            for (int k = 0; k < nf; ++k) {
+                                const float fr = (float)(1 << k);
+                                acc += fr * (Weff[c * RP + o_ray + 3 + 6 * k + d] * cosf(dv * fr) - Weff[c * RP + o_ray + 6 + 6 * k + d] * sinf(dv * fr));
+                            }
+                            dirg[d] += acc * pbar[c];
+                        }
+                    }
+                }
+                if (a.p.xyz) {
+                    if (a.ig.d_xyz) { a.ig.d_xyz[3 * i] = dx[0]; a.ig.d_xyz[3 * i + 1] = dx[1]; a.ig.d_xyz[3 * i + 2] = dx[2]; }
+                    if (a.ig.d_ray && rad) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) atomicAdd(a.ig.d_ray + 3 * ray_id + d, dirg[d]);
+                    }
+                } else {
+                    const int j = (int)(i_in - (int64_t)ray_id * a.p.n_per_ray);
+                    const float tv = __ldg(a.p.t + (int64_t)ray_id * a.p.t_stride + a.p.t_offset + j);
+                    if (a.ig.d_center) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) atomicAdd(a.ig.d_center + 3 * ray_id + d, dx[d]);
+                    }
+                    if (a.ig.d_ray) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) atomicAdd(a.ig.d_ray + 3 * ray_id + d, tv * dx[d] + dirg[d]);
+                    }
+                    if (a.ig.d_t) {
+                        float dt = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) dt += __ldg(a.p.ray + 3 * ray_id + d) * dx[d];
+                        a.ig.d_t[i_in] = dt;
                     }
                 }
             }

@@ -124,7 +124,8 @@ __global__ void ls_composite_backward_kernel(const float* __restrict__ ray, cons
                                              const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
                                              const float* __restrict__ g_normal, float* __restrict__ d_sdf,
                                              float* __restrict__ d_rgbs, float* __restrict__ d_nrm,
-                                             float* __restrict__ d_beta_param, float* __restrict__ d_ray) {
+                                             float* __restrict__ d_beta_param, float* __restrict__ d_ray,
+                                             float* __restrict__ d_t) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= n_rays) return;
@@ -177,6 +178,7 @@ __global__ void ls_composite_backward_kernel(const float* __restrict__ ray, cons
     op = ls_warp_sum(op);
     float pre = 0.f;          // running inclusive prefix of c_i w_i
     float dbeta = 0.f, drlen = 0.f;
+    float qcarry = 0.f;       // d L / d (t_{i+1} - t_i) of the last interval of the previous chunk
 #pragma unroll
     for (int ch = 0; ch < LS_MAX_CHUNKS; ++ch) {
         if (ch * 32 < N - 1) {
@@ -185,6 +187,17 @@ __global__ void ls_composite_backward_kernel(const float* __restrict__ ray, cons
             const float incl = ls_warp_incl_scan(cw[ch], lane);
             const float S = Csum - (pre + incl);           // sum_{j>i} c_j w_j
             pre += __shfl_sync(0xffffffffu, incl, 31);
+            if (d_t) {      // depths: t_i enters the depth output directly and the interval lengths (t_{i+1} - t_i) |ray|
+                float q = 0.f;
+                if (on) q = (cc[ch] * Tn[ch] - S) * ls_sdf_to_sigma(sr[i], alpha, beta) * rlen;
+                float qprev = __shfl_up_sync(0xffffffffu, q, 1);
+                if (lane == 0) qprev = qcarry;
+                qcarry = __shfl_sync(0xffffffffu, q, 31);
+                if (on) {
+                    d_t[(int64_t)r * N + i] = gd * w[ch] - q + qprev;
+                    if (i == N - 2) d_t[kl] = gd * (1.f - op) + q;
+                }
+            }
             if (on) {
                 const int64_t k = (int64_t)r * N + i;
                 const float dsd = cc[ch] * Tn[ch] - S;

@@ -54,7 +54,7 @@ class RadF(nn.Module):
     # ------------------------------------------------------------------ reference surface
     def Geometry_feat(self, xyz):
         shp = xyz.shape[:-1]
-        flat = xyz.detach().reshape(-1, 3).float()
+        flat = xyz.reshape(-1, 3).float()
         _, y, _, _ = ops.FieldEval.apply(self.field_spec(), None, self.embed_fn.embedder_obj.params, self.Geo_enc.theta(),
                                          None, None, None, flat, None, None, None, 0, None, True, False)
         return y.view(*shp, -1)

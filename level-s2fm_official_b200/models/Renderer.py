@@ -48,17 +48,30 @@ class Renderer:
         return {"theta": theta, "w_eff": w_eff, "b_eff": b_eff, "image": image}
 
     def volsdf_sampling(self, opt, center, ray, SDF_Field, det=True, prepared=None):
-        """Depth samples [B,R,N] (returned three times like the reference's default branch)."""
+        """Depth samples [B,R,N] (returned three times like the reference's default branch).
+
+        Gradients: the reference's RayAABBIntersector defines no backward (utils/custom_functions.py:10-31), so a loss that
+        reaches grad-requiring rays through the uniform depths raises there.  Here the slab test has its analytic VJP
+        (``ops.UniformDepths``; SURVEY 8a defect iii) unless ``opt.Renderer.aabb_grad`` is set to False, in which case the
+        reference's behaviour (NotImplementedError) is reproduced.  The error-bounded branch runs under no_grad in the
+        reference (models/Renderer.py:185) and yields constant depths here too."""
         B, R = center.shape[:2]
-        c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
         v = opt.SDF.VolSDF
         if v.volsdf_sampling == True:   # noqa: E712
             from .. import sampler
+            c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
             prepared = prepared or self._prepare(SDF_Field)
             t, beta_plus, iters = sampler.error_bounded(self, opt, c2, r2, SDF_Field, prepared)
             return t.view(B, R, -1), beta_plus.view(B, R), iters.view(B, R)
-        t, _ = ops.sample_uniform_raw(_C.get(), c2, r2, int(v.sample_intvs), [float(x) for x in opt.data.bound_min],
-                                      [float(x) for x in opt.data.bound_max])
+        bmin, bmax = [float(x) for x in opt.data.bound_min], [float(x) for x in opt.data.bound_max]
+        if torch.is_grad_enabled() and (center.requires_grad or ray.requires_grad):
+            if getattr(getattr(opt, "Renderer", None), "aabb_grad", True) == False:   # noqa: E712
+                raise NotImplementedError("RayAABBIntersector has no backward in the reference (utils/custom_functions.py:10-31); "
+                                          "set opt.Renderer.aabb_grad = True for the analytic slab-test gradient")
+            t = ops.UniformDepths.apply(center.reshape(-1, 3).float(), ray.reshape(-1, 3).float(), int(v.sample_intvs), bmin, bmax)
+        else:
+            c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
+            t, _ = ops.sample_uniform_raw(_C.get(), c2, r2, int(v.sample_intvs), bmin, bmax)
         t = t.view(B, R, -1)
         return t, t, t
 
@@ -69,12 +82,17 @@ class Renderer:
         return self.render_with_depths(opt, center, ray, t, SDF_Field, Rad_Field, prepared=prepared)
 
     def render_with_depths(self, opt, center, ray, t, SDF_Field, Rad_Field, prepared=None):
-        """Everything of Renderer.forward after the depth sampler (models/Renderer.py:57-116) for given depths t [B,R,N]."""
+        """Everything of Renderer.forward after the depth sampler (models/Renderer.py:57-116) for given depths t [B,R,N].
+        Differentiable w.r.t. the field parameters and w.r.t. center / ray / t (sample positions x = center + ray t, the Fourier
+        embedding of the direction and the interval lengths |ray| dt)."""
+        if SDF_Field._bg_sdf():
+            raise NotImplementedError("opt.data.bg_sdf (background-sphere clamp, models/SDF.py:68-69) is not fused into the render "
+                                      "kernels; no shipped config sets it")
         prepared = prepared or self._prepare(SDF_Field, Rad_Field)
         B, R = center.shape[:2]
         N = t.shape[-1]
-        c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
-        t2 = t.reshape(B * R, N).contiguous()
+        c2, r2 = center.reshape(-1, 3).float(), ray.reshape(-1, 3).float()
+        t2 = t.reshape(B * R, N)
         geo2 = None
         if Rad_Field.dual_field:
             _, geo2, _, _ = ops.FieldEval.apply(Rad_Field.field_spec(), None, Rad_Field.embed_fn.embedder_obj.params,
@@ -83,8 +101,7 @@ class Renderer:
         sdf, _, nrm, rgbs = ops.FieldEval.apply(SDF_Field.field_spec(), Rad_Field.rad_spec(), SDF_Field.table(),
                                                 prepared["theta"], prepared["w_eff"], prepared["b_eff"], geo2, None, c2, r2, t2,
                                                 0, None, False, True, prepared["image"])
-        ray_in = ray.reshape(-1, 3).float() if ray.requires_grad else r2
-        rgb, depth, normal, _ = ops.Composite.apply(ray_in, t2, sdf.view(B * R, N), rgbs.view(B * R, N, 3),
+        rgb, depth, normal, _ = ops.Composite.apply(r2, t2, sdf.view(B * R, N), rgbs.view(B * R, N, 3),
                                                     nrm.view(B * R, N, 3), SDF_Field.beta, float(SDF_Field.beta_speed),
                                                     self._bg)
         return {"rgb": rgb.view(B, R, 3), "sdfs_volume": sdf.view(B, R, N, 1), "normals": nrm.view(B, R, N, 3),

@@ -49,15 +49,27 @@ class SDF(nn.Module):
     def table(self):
         return self.embed_fn.embedder_obj.params
 
-    def _eval(self, xyz, want_y=False, want_nrm=False):
+    def _bg_sdf(self) -> bool:
+        return self.opt.data.inside == True and getattr(self.opt.data, "bg_sdf", False) == True  # noqa: E712
+
+    def _eval(self, xyz, want_y=False, want_nrm=False, sdf_x_detached=False):
+        """One fused launch: sdf [...,1], raw MLP output [...,k+1] | None, d sdf / d x [...,3] | None.  Differentiable w.r.t. the
+        field parameters AND the positions (like tcnn's encoding in the reference)."""
         shp = xyz.shape[:-1]
-        flat = xyz.detach().reshape(-1, 3).float()
+        flat = xyz.reshape(-1, 3).float()
         sdf, y, nrm, _ = ops.FieldEval.apply(self.field_spec(), None, self.table(), self.SDF_MLP.theta(), None, None, None,
-                                             flat, None, None, None, 0, None, want_y, want_nrm)
+                                             flat, None, None, None, 0, None, want_y, want_nrm, None, sdf_x_detached)
         sdf = sdf.view(*shp, 1)
-        if self.opt.data.inside == True and getattr(self.opt.data, "bg_sdf", False) == True:  # noqa: E712
-            sdf = torch.min(sdf, self.opt.data.bg_rad - xyz.detach().norm(dim=-1, keepdim=True))
-        return sdf, (y.view(*shp, -1) if want_y else None), (nrm.view(*shp, 3) if want_nrm else None)
+        nrm = nrm.view(*shp, 3) if want_nrm else None
+        if self._bg_sdf():
+            # min(sdf, bg_rad - |x|) (models/SDF.py:68-69); where the sphere term is active its gradient is -x/|x|
+            xs = xyz.detach() if sdf_x_detached else xyz
+            r = xs.norm(dim=-1, keepdim=True)
+            bg = self.opt.data.bg_rad - r
+            if nrm is not None:
+                nrm = torch.where(bg < sdf, -xyz / xyz.norm(dim=-1, keepdim=True), nrm)
+            sdf = torch.min(sdf, bg)
+        return sdf, (y.view(*shp, -1) if want_y else None), nrm
 
     # ------------------------------------------------------------------ reference surface
     def infer_sdf(self, xyz, mode="ret_sdf"):
@@ -83,18 +95,23 @@ class SDF(nn.Module):
         return self.sdf_to_sigma(self.infer_sdf(xyzs), alpha, beta)
 
     def gradient(self, p):
-        """d sdf / d p by the kernel's analytic reverse sweep.  Like the reference (create_graph=True) the result
-        stays differentiable w.r.t. the field parameters."""
-        p.requires_grad_(True)
-        return self._eval(p, want_nrm=True)[2]
+        """d sdf / d p by the kernel's analytic reverse sweep (models/SDF.py:102-114).  Like the reference
+        (create_graph=True) the result stays differentiable w.r.t. the field parameters and w.r.t. ``p`` itself
+        (``p.requires_grad_`` is set in place on the caller's tensor, as the reference does)."""
+        with torch.enable_grad():
+            p.requires_grad_(True)
+            return self._eval(p, want_nrm=True)[2]
 
     def sdf_and_gradient(self, p):
         sdf, _, nrm = self._eval(p, want_nrm=True)
         return sdf, nrm
 
     def get_surface_pts(self, pts):
-        """One Newton projection onto the zero level set (models/SDF.py:95-100); one fused launch."""
-        sdf, normals = self.sdf_and_gradient(pts)
+        """One Newton projection onto the zero level set (models/SDF.py:95-100); one fused launch.  As in the reference the sdf
+        is evaluated at ``pts.detach()`` and the normals at ``pts`` (which gets requires_grad set in place)."""
+        with torch.enable_grad():
+            pts.requires_grad_(True)
+            sdf, _, normals = self._eval(pts, want_nrm=True, sdf_x_detached=True)
         normals_value = torch.norm(normals, dim=-1, keepdim=True)
         surf_pts = pts - normals / normals_value.detach() * sdf
         return surf_pts, normals_value

@@ -122,8 +122,11 @@ class Embedder_Fourier(nn.Module):
         else:
             self.freq_bands = torch.linspace(2.0 ** 0.0, 2.0 ** max_freq_log2, N_freqs)
 
-    def forward(self, input):
-        out = [input] if self.include_input else []
+    def forward(self, input, bound_min=None, bound_max=None, rescale=1.0):
+        """Same signature as the reference (models/base.py:75-97): the bounds are accepted and unused, the raw input is divided
+        by ``rescale``."""
+        assert input.shape[-1] == self.input_dim
+        out = [input / rescale] if self.include_input else []
         for f in self.freq_bands.tolist():
             for fn in self.periodic_fns:
                 out.append(fn(input * f))

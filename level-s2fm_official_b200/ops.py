@@ -226,15 +226,23 @@ def field_forward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: O
 
 def field_backward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: Optional[_C.Radiance],
                        g_y, g_sdf, g_nrm, g_rgb, saved_nrm, saved_rgb,
-                       d_table, d_theta, d_w_eff=None, d_b_eff=None, d_geo2=None, image=None, mode="auto"):
+                       d_table, d_theta, d_w_eff=None, d_b_eff=None, d_geo2=None, image=None, mode="auto",
+                       d_xyz=None, d_center=None, d_ray=None, d_t=None):
     """image: the operand image of field_prepare_raw for the SAME theta -- with it large launches run the tensor-core kernel.
-    mode: "auto" (library dispatch) | "simt" (exact fp32 kernel) | "tc" (tensor-core kernel or an error)."""
+    mode: "auto" (library dispatch) | "simt" (exact fp32 kernel) | "tc" (tensor-core kernel or an error).
+    d_xyz (explicit points, written) / d_center, d_ray (+=), d_t (written) (ray mode): gradients w.r.t. the sample positions."""
     f = spec.c_field(lib, table, theta, image)
+    ig = None
+    if d_xyz is not None or d_center is not None or d_ray is not None or d_t is not None:
+        ig = _C.InputGrads()
+        ig.d_xyz, ig.d_center, ig.d_ray, ig.d_t = lib.ptr(d_xyz), lib.ptr(d_center), lib.ptr(d_ray), lib.ptr(d_t)
+        if mode == "tc":
+            mode = "auto"   # position gradients come from the fp32-SIMT kernel
     if mode == "tc" and (image is None or (g_nrm is None and g_rgb is None)):
         mode = "auto"       # no operand image / no gradient on the normals: nothing for the tensor-core kernel to do
     name = {"auto": "field_backward", "simt": "field_backward_simt", "tc": "field_backward_tc"}[mode]
     _call(lib, name, getattr(lib.dll, "ls2fm_" + name), f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
-        lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), lib.stream())
+        lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), ig, lib.stream())
 
 
 def grid_encode_raw(lib, grid: GridSpec, table, u, want_idx=False):
@@ -285,7 +293,7 @@ def composite_forward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, b
 
 
 def composite_backward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bgcolor, g_rgb, g_depth, g_normal,
-                           want_d_ray=False):
+                           want_d_ray=False, want_d_t=False):
     r, n = t.shape
     dev = t.device
     d_sdf = torch.empty(r, n, device=dev)
@@ -293,10 +301,11 @@ def composite_backward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, 
     d_nrm = torch.empty(r, n, 3, device=dev) if nrm is not None else None
     d_beta = torch.zeros(1, device=dev)
     d_ray = torch.zeros(r, 3, device=dev) if want_d_ray else None
+    d_t = torch.empty(r, n, device=dev) if want_d_t else None
     _call(lib, "composite_backward", lib.dll.ls2fm_composite_backward, lib.ptr(ray), lib.ptr(t), lib.ptr(sdf), lib.ptr(rgbs), lib.ptr(nrm), lib.ptr(beta_param), float(beta_speed),
         _C.f3(bgcolor), r, n, lib.ptr(g_rgb), lib.ptr(g_depth), lib.ptr(g_normal),
-        lib.ptr(d_sdf), lib.ptr(d_rgbs), lib.ptr(d_nrm), lib.ptr(d_beta), lib.ptr(d_ray), lib.stream())
-    return d_sdf, d_rgbs, d_nrm, d_beta, d_ray
+        lib.ptr(d_sdf), lib.ptr(d_rgbs), lib.ptr(d_nrm), lib.ptr(d_beta), lib.ptr(d_ray), lib.ptr(d_t), lib.stream())
+    return d_sdf, d_rgbs, d_nrm, d_beta, d_ray, d_t
 
 
 # ------------------------------------------------------------------------- autograd
@@ -307,23 +316,42 @@ def _c(t):
     return None if t is None else t.contiguous()
 
 
+def grad_sink(param):
+    """The buffer the fused backward may accumulate into directly for this parameter, or None.
+
+    ``parallel.GradBucket`` (or any caller that owns ``param.grad`` as a persistent, pre-zeroed buffer and only ever calls
+    ``loss.backward()``) sets ``param._ls2fm_grad_sink = param.grad``: the table-gradient scatter then lands in the bucket itself
+    instead of a fresh zero-filled 49 MB tensor that autograd adds to ``.grad`` afterwards (two extra passes over the table
+    per backward).  Not valid under ``torch.autograd.grad`` -- which is why it is opt-in."""
+    sink = getattr(param, "_ls2fm_grad_sink", None)
+    if sink is not None and (sink.shape != param.shape or sink.device != param.device or not sink.is_contiguous()):
+        return None
+    return sink
+
+
 class FieldEval(torch.autograd.Function):
     """Fused hash grid + geometry MLP (+ analytic normals, + radiance).
 
-    Differentiable w.r.t. ``table``, ``theta``, ``w_eff``, ``b_eff`` and ``geo2`` -- including the
-    second-order path through the normals (the reference's SDF.gradient uses create_graph=True,
-    models/SDF.py:107-113).  Not differentiable w.r.t. the sample positions (see include/ls2fm.h).
+    Differentiable w.r.t. ``table``, ``theta``, ``w_eff``, ``b_eff``, ``geo2`` -- including the second-order path through the
+    normals (the reference's SDF.gradient uses create_graph=True, models/SDF.py:107-113) -- and w.r.t. the sample positions:
+    ``xyz`` (explicit points) or ``center`` / ``ray`` / ``t`` (ray mode, x = center + ray * t), as tiny-cuda-nn's encoding is in
+    the reference (pipelines/BA.py:123-125 feeds get_surface_pts' output back into infer_sdf; SDF.gradient is differentiated
+    w.r.t. p).  The position gradient itself is first-order (no double backward through it).
 
     forward(spec, rad_spec, table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, t_offset, n_per_ray,
-            want_y, want_nrm) -> (sdf [n], y [n,dout] | empty, nrm [n,3] | empty, rgb [n,3] | empty)
+            want_y, want_nrm, image=None, sdf_x_detached=False)
+        -> (sdf [n], y [n,dout] | empty, nrm [n,3] | empty, rgb [n,3] | empty)
+    sdf_x_detached: the sdf output is treated as a function of the DETACHED positions (get_surface_pts evaluates
+    ``infer_sdf(pts.detach())`` next to ``gradient(pts)``, models/SDF.py:96-97) while sharing one launch with the normals.
     """
 
     @staticmethod
     def forward(ctx, spec, rad_spec, table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, t_offset, n_per_ray,
-                want_y, want_nrm, image=None):
+                want_y, want_nrm, image=None, sdf_x_detached=False):
         lib = _C.get()
+        ctx.table_sink = grad_sink(table)
         table, theta = table.detach().contiguous(), theta.detach().contiguous()
-        xyz, center, ray, t = _c(xyz), _c(center), _c(ray), _c(t)
+        xyz, center, ray, t = (_c(v.detach()) if v is not None else None for v in (xyz, center, ray, t))
         with_rad = w_eff is not None
         if with_rad:
             w_eff, b_eff = w_eff.detach().contiguous(), b_eff.detach().contiguous()
@@ -336,7 +364,9 @@ class FieldEval(torch.autograd.Function):
         ctx.pt_args = (t_offset, n_per_ray)
         ctx.with_rad, ctx.want_y, ctx.want_nrm = with_rad, want_y, want_nrm
         ctx.image = image
-        ctx.save_for_backward(table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, nrm if with_rad else None, rgb)
+        ctx.sdf_x_detached = bool(sdf_x_detached)
+        keep_nrm = with_rad or (sdf_x_detached and nrm is not None)
+        ctx.save_for_backward(table, theta, w_eff, b_eff, geo2, xyz, center, ray, t, nrm if keep_nrm else None, rgb)
         out_y = y if want_y else table.new_empty(0)
         out_nrm = nrm if (want_nrm or with_rad) else table.new_empty(0)
         out_rgb = rgb if with_rad else table.new_empty(0)
@@ -355,32 +385,63 @@ class FieldEval(torch.autograd.Function):
         g_nrm = _c(g_nrm) if ((ctx.want_nrm or ctx.with_rad) and g_nrm is not None) else None
         g_rgb = _c(g_rgb) if with_rad else None
         g_sdf = _c(g_sdf) if g_sdf is not None else None
-        d_table = torch.zeros_like(table)
-        d_theta = torch.zeros_like(theta)
+        need = ctx.needs_input_grad
+        sink = ctx.table_sink if need[2] else None
+        d_table = sink if sink is not None else (torch.zeros_like(table) if need[2] else None)
+        d_theta = torch.zeros_like(theta) if need[3] else None
         d_w = torch.zeros_like(w_eff) if with_rad else None
         d_b = torch.zeros_like(b_eff) if with_rad else None
         d_geo2 = torch.empty_like(geo2) if (with_rad and geo2 is not None) else None
-        field_backward_raw(lib, spec, table, theta, pts, rad, g_y, g_sdf, g_nrm, g_rgb, s_nrm, s_rgb,
-                           d_table, d_theta, d_w, d_b, d_geo2, image=ctx.image, mode=BACKWARD_MODE)
-        return (None, None, d_table, d_theta, d_w, d_b, d_geo2, None, None, None, None, None, None, None, None, None)
+        d_xyz = d_center = d_ray = d_t = None
+        if xyz is not None:
+            if need[7]:
+                d_xyz = torch.empty_like(xyz)
+            if need[9] and ray is not None and with_rad:
+                d_ray = torch.zeros_like(ray)
+        else:
+            if need[8]:
+                d_center = torch.zeros_like(center)
+            if need[9]:
+                d_ray = torch.zeros_like(ray)
+            if need[10]:
+                t_off, npr = ctx.pt_args
+                if t_off != 0 or (npr is not None and npr != t.shape[-1]):
+                    raise NotImplementedError("gradient w.r.t. a column slice of t")
+                d_t = torch.empty_like(t)
+        field_backward_raw(lib, spec, table, theta, pts, rad, g_y, g_sdf, g_nrm, g_rgb, s_nrm if with_rad else None, s_rgb,
+                           d_table, d_theta, d_w, d_b, d_geo2, image=ctx.image, mode=BACKWARD_MODE,
+                           d_xyz=d_xyz, d_center=d_center, d_ray=d_ray, d_t=d_t)
+        if d_xyz is not None and ctx.sdf_x_detached and g_sdf is not None:
+            d_xyz = d_xyz - g_sdf.reshape(-1, 1) * s_nrm          # d sdf / d x == the forward normal
+        return (None, None, None if sink is not None else d_table, d_theta, d_w, d_b, d_geo2, d_xyz, d_center, d_ray, d_t,
+                None, None, None, None, None, None)
 
 
 class Composite(torch.autograd.Function):
     """Laplace-CDF density + alpha compositing + background fill (models/Renderer.py:33-49,80-107).
 
-    forward(ray [R,3], t [R,N], sdf [R,N], rgbs [R,N,3], nrm [R,N,3], beta_param [1], beta_speed, bgcolor)
+    forward(ray [R,3], t [R,N], sdf [R,N], rgbs [R,N,3] | None, nrm [R,N,3] | None, beta_param [1], beta_speed, bgcolor)
         -> rgb [R,3], depth [R], normal [R,3], opacity [R]
+    Differentiable w.r.t. sdf, rgbs, nrm, beta_param, ray (interval lengths |ray| dt) and t.
     """
 
     @staticmethod
     def forward(ctx, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bgcolor):
         lib = _C.get()
-        ray, t, sdf, rgbs, nrm = _c(ray.detach()), _c(t.detach()), _c(sdf.detach()), _c(rgbs.detach()), _c(nrm.detach())
+        ray, t, sdf = _c(ray.detach()), _c(t.detach()), _c(sdf.detach())
+        rgbs = _c(rgbs.detach()) if rgbs is not None else None
+        nrm = _c(nrm.detach()) if nrm is not None else None
         beta_param = beta_param.detach().contiguous()
         rgb, depth, normal, opacity = composite_forward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bgcolor)
         ctx.save_for_backward(ray, t, sdf, rgbs, nrm, beta_param)
         ctx.misc = (beta_speed, tuple(bgcolor))
         ctx.mark_non_differentiable(opacity)
+        if rgb is None:
+            rgb = t.new_empty(0)
+            ctx.mark_non_differentiable(rgb)
+        if normal is None:
+            normal = t.new_empty(0)
+            ctx.mark_non_differentiable(normal)
         return rgb, depth, normal, opacity
 
     @staticmethod
@@ -388,10 +449,51 @@ class Composite(torch.autograd.Function):
         lib = _C.get()
         ray, t, sdf, rgbs, nrm, beta_param = ctx.saved_tensors
         beta_speed, bg = ctx.misc
-        want_ray = ctx.needs_input_grad[0]
-        d_sdf, d_rgbs, d_nrm, d_beta, d_ray = composite_backward_raw(
-            lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bg, _c(g_rgb), _c(g_depth), _c(g_normal), want_ray)
-        return d_ray, None, d_sdf, d_rgbs, d_nrm, d_beta.view_as(beta_param), None, None
+        want_ray, want_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        d_sdf, d_rgbs, d_nrm, d_beta, d_ray, d_t = composite_backward_raw(
+            lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bg, _c(g_rgb) if rgbs is not None else None, _c(g_depth),
+            _c(g_normal) if nrm is not None else None, want_ray, want_t)
+        return d_ray, d_t, d_sdf, d_rgbs, d_nrm, d_beta.view_as(beta_param), None, None
+
+
+class UniformDepths(torch.autograd.Function):
+    """Ray / AABB slab test + Renderer.sample_depth (models/Renderer.py:118-127,178-185) as ONE launch, with the analytic VJP the
+    reference's RayAABBIntersector lacks (utils/custom_functions.py:10-31; SURVEY 8a defect iii): on the slab axis that decides
+    t_near / t_far, dt/do_k = -1/d_k and dt/dd_k = -t/d_k; zero where t_near was clamped to 0 or the ray misses the box.
+
+    forward(center [R,3], ray [R,3], n_samples, bound_min, bound_max) -> t [R,N]"""
+
+    @staticmethod
+    def forward(ctx, center, ray, n_samples, bound_min, bound_max):
+        lib = _C.get()
+        c, r = _c(center.detach()), _c(ray.detach())
+        t, hits = sample_uniform_raw(lib, c, r, n_samples, bound_min, bound_max)
+        ctx.save_for_backward(c, r, hits)
+        ctx.misc = (n_samples, tuple(bound_min), tuple(bound_max))
+        return t
+
+    @staticmethod
+    def backward(ctx, g_t):
+        c, r, hits = ctx.saved_tensors
+        n, bmin, bmax = ctx.misc
+        frac = (torch.arange(n, device=g_t.device, dtype=g_t.dtype) + 0.5) / n
+        g_far = (g_t * frac).sum(-1)
+        g_near = g_t.sum(-1) - g_far
+        lo_p = torch.tensor(bmin, device=c.device, dtype=c.dtype)
+        hi_p = torch.tensor(bmax, device=c.device, dtype=c.dtype)
+        inv = 1.0 / r
+        t_lo, t_hi = (lo_p - c) * inv, (hi_p - c) * inv
+        k_near = torch.minimum(t_lo, t_hi).argmax(dim=-1, keepdim=True)
+        k_far = torch.maximum(t_lo, t_hi).argmin(dim=-1, keepdim=True)
+        hit = hits[:, 1] > 0
+        g_near = torch.where(hit & (hits[:, 0] > 0), g_near, torch.zeros_like(g_near))
+        g_far = torch.where(hit, g_far, torch.zeros_like(g_far))
+        d_c, d_r = torch.zeros_like(c), torch.zeros_like(r)
+        for k, g, tv in ((k_near, g_near, hits[:, 0]), (k_far, g_far, hits[:, 1])):
+            inv_k = inv.gather(-1, k)[:, 0]
+            d_c.scatter_add_(-1, k, (-g * inv_k)[:, None])
+            d_r.scatter_add_(-1, k, (-g * tv * inv_k)[:, None])
+        return d_c, d_r, None, None, None
 
 
 class GridEncode(torch.autograd.Function):
@@ -548,6 +650,8 @@ class GenerateRays(torch.autograd.Function):
         lib = _C.get()
         pose_c, kinv_c, xy_c = pose.detach().contiguous().float(), kinv.detach().contiguous().float(), xy.detach().contiguous().float()
         B, N = pose_c.shape[0], xy_c.shape[0]
+        if tuple(kinv_c.shape) != (B, 3, 3) or tuple(pose_c.shape) != (B, 3, 4):
+            raise ValueError(f"GenerateRays: pose {tuple(pose_c.shape)} / kinv {tuple(kinv_c.shape)}: need [B,3,4] and [B,3,3]")
         center = torch.empty(B, N, 3, device=pose.device)
         ray = torch.empty(B, N, 3, device=pose.device)
         _call(lib, "generate_rays", lib.dll.ls2fm_generate_rays, lib.ptr(pose_c), lib.ptr(kinv_c), lib.ptr(xy_c), B, N,

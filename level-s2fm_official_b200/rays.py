@@ -22,6 +22,10 @@ def get_center_and_ray(opt, pose, intr=None, rays_idx=None, xy_grid=None):
     with torch.no_grad():
         xy = mesh_grid(opt) if xy_grid is None else xy_grid[rays_idx, :]
         kinv = intr.inverse()
-    if kinv.dim() == 2:
-        kinv = kinv[None].expand(len(pose), 3, 3)
+    # the reference broadcasts the intrinsics through a matmul: its own callers pass intr[None] ([1,3,3]) next to a
+    # multi-camera pose [B,3,4] (pipelines/Camera.py:472); the kernel indexes one K^-1 per camera
+    kinv = kinv.reshape(-1, 3, 3)
+    if kinv.shape[0] not in (1, len(pose)):
+        raise ValueError(f"intr has {kinv.shape[0]} matrices for {len(pose)} cameras")
+    kinv = kinv.expand(len(pose), 3, 3).contiguous()
     return ops.GenerateRays.apply(pose, kinv, xy)

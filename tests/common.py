@@ -96,3 +96,22 @@ def rel_err(a, b):
 
 def cosine(a, b):
     return torch.nn.functional.cosine_similarity(a.reshape(-1).double(), b.reshape(-1).double(), dim=0).item()
+
+
+def cell_ids(x, cfg):
+    """Integer cell coordinates of world points x [M,3] at every hash-grid level -> int64 [M, L, 3] (the floor() of SURVEY A.1).
+    The field is trilinear INSIDE a cell: its gradient jumps across cell faces, so two evaluations of the 'same' point that
+    differ by an ulp can legitimately return different normals iff their cell ids differ at some level."""
+    bmin = torch.tensor(cfg.bound_min, dtype=x.dtype)
+    bmax = torch.tensor(cfg.bound_max, dtype=x.dtype)
+    u = ((x - bmin) / (bmax - bmin)).reshape(-1, 3)
+    out = []
+    for lvl in cfg.grid().levels:
+        p = (u.double() * lvl.scale + 0.5).float()
+        out.append(torch.floor(p).to(torch.int64))
+    return torch.stack(out, dim=1)
+
+
+def same_cells(xa, xb, cfg):
+    """bool [M]: both point sets fall into the same cell at every level."""
+    return (cell_ids(xa, cfg) == cell_ids(xb, cfg)).all(dim=-1).all(dim=-1)

@@ -320,3 +320,36 @@ def test_fused_param_prep_matches_torch_weight_norm_and_composition(layers, dual
 
 def test_ray_generation_kernel_matches_oracle():
     gc.rays_case(DEV)
+
+
+# ----------------------------------------------------------------------------- gradients w.r.t. the sample positions
+def test_position_gradient_first_order():
+    from . import input_grad_checks as ig
+    ig.first_order(DEV, n=3000)
+
+
+def test_position_gradient_of_the_normals():
+    from . import input_grad_checks as ig
+    ig.hessian_vector(DEV, n=2000)
+
+
+@pytest.mark.parametrize("dataset", ["DTU", "ETH3D", "bmvs"])
+def test_ba_surface_point_pattern_gradients(dataset):
+    from . import input_grad_checks as ig
+    ig.ba_surface_pattern(DEV, n=2500, dataset=dataset)
+
+
+@pytest.mark.parametrize("dataset,dual", [("DTU", False), ("bmvs", True), ("ETH3D", False)])
+def test_pose_gradient_through_renderer(dataset, dual):
+    from . import input_grad_checks as ig
+    ig.pose_gradient_through_renderer(DEV, dataset, dual, n_pix=40, n_samples=24)
+
+
+def test_aabb_grad_flag_reproduces_reference_error():
+    from . import input_grad_checks as ig
+    ig.aabb_grad_flag(DEV)
+
+
+def test_radf_geometry_feat_position_gradient():
+    from . import input_grad_checks as ig
+    ig.radf_geometry_feat_input_grad(DEV, n=1000)

@@ -95,7 +95,7 @@ def test_forced_tensor_core_backward_refuses_what_it_cannot_do(hostsim_lib):
         f = spec.c_field(hostsim_lib, table, theta, image)
         ops._call(hostsim_lib, "field_backward_tc", hostsim_lib.dll.ls2fm_field_backward_tc, f, pts, None, None, hostsim_lib.ptr(g),
                   hostsim_lib.ptr(g_nrm), None, None, None, hostsim_lib.ptr(d_table), hostsim_lib.ptr(d_theta), None, None, None,
-                  hostsim_lib.stream())
+                  None, hostsim_lib.stream())
 
     with pytest.raises(RuntimeError, match="field_backward_tc"):      # no operand image
         forced_tc(None, gn0)
@@ -261,3 +261,36 @@ def test_fused_param_prep_matches_torch_weight_norm_and_composition(layers, dual
 
 def test_ray_generation_kernel_matches_oracle():
     gc.rays_case("cpu")
+
+
+# ----------------------------------------------------------------------------- gradients w.r.t. the sample positions
+def test_position_gradient_first_order():
+    from . import input_grad_checks as ig
+    ig.first_order("cpu", n=120)
+
+
+def test_position_gradient_of_the_normals():
+    from . import input_grad_checks as ig
+    ig.hessian_vector("cpu", n=90)
+
+
+@pytest.mark.parametrize("dataset", ["DTU", "ETH3D"])
+def test_ba_surface_point_pattern_gradients(dataset):
+    from . import input_grad_checks as ig
+    ig.ba_surface_pattern("cpu", n=150, dataset=dataset)
+
+
+@pytest.mark.parametrize("dataset,dual", [("DTU", False), ("bmvs", True)])
+def test_pose_gradient_through_renderer(dataset, dual):
+    from . import input_grad_checks as ig
+    ig.pose_gradient_through_renderer("cpu", dataset, dual, n_pix=6, n_samples=10)
+
+
+def test_aabb_grad_flag_reproduces_reference_error():
+    from . import input_grad_checks as ig
+    ig.aabb_grad_flag("cpu")
+
+
+def test_radf_geometry_feat_position_gradient():
+    from . import input_grad_checks as ig
+    ig.radf_geometry_feat_input_grad("cpu", n=60)
