@@ -291,12 +291,39 @@ int ls2fm_sphere_trace(const ls2fm_field_t* sdf_field, const float* ray0, const 
 int ls2fm_render_loss(const float* rgb, const float* gt, int64_t n_rays, const float* normals, int64_t n_samples,
                       float w_rgb, float w_eik, float* sums, float* g_rgb, float* g_normals, void* stream);
 
+/* The whole loss tail of CameraSet.render + the stage's compute_loss (pipelines/Camera.py:506-537, BA.py:190-204,
+ * rendering_refine.py:99-107) in two launches:
+ *   mask_bg [R] u8 (written) = 0.05 < mean(gt) < 0.95;  mask_finish [R] u8 (written) = mask_finish_in & mask_bg (0 when mask_finish_in is NULL)
+ *   sums [8] (zeroed by the call): [0] sum |rgb - gt| over R*3, [1] sum | ||n|| - 1 | over the counted samples, [2] #mask_bg rays,
+ *        [3] sum (rgb - gt)^2 over the mask_bg rays (PSNR = -10 log10(sums[3] / (3 sums[2]))), [4] sum smooth_l1(d_points - depth_mlp)
+ *        over the mask_finish rays, [5] #mask_finish rays
+ *   eik_masked = 1: the eikonal term runs over the samples of mask_bg rays only (BA.py:192-193); 0: over all samples
+ *   gradients of  w_rgb * mean_L1 + w_eik * mean_eikonal + w_dc * mean_smooth_l1  (each mean over its own count; the DC term is 0
+ *   when no ray is finished): g_rgb [R,3], g_depth [R], g_dpoints [R], g_normals [R*n_per_ray,3]; all nullable.
+ * depth_mlp / d_points (both or neither) and normals are nullable inputs. */
+int ls2fm_render_tail(const float* rgb, const float* gt, const float* depth_mlp, const float* d_points, const uint8_t* mask_finish_in,
+                      const float* normals, int64_t n_rays, int32_t n_per_ray, int32_t eik_masked, float w_rgb, float w_eik, float w_dc,
+                      float* sums, uint8_t* mask_bg, uint8_t* mask_finish, float* g_rgb, float* g_depth, float* g_dpoints, float* g_normals,
+                      void* stream);
+
+/* ------------------------------------------------------------------ marching-cubes query grid
+ * The N^3 query points of utils/util.py:392-411 (extract_mesh) for flat indices [begin, begin + count), written to
+ * xyz [count,3]: same float64 arithmetic as the reference's numpy code (true division included), cast to float32.
+ * step = volume_size / (N - 1); origin = (voxel_grid_origin[2], [1], [0]) -- the reference's own order.  Feed the chunk
+ * to ls2fm_field_forward (values only) -- replaces 8192 host-side chunks + H2D/D2H copies of a 512^3 grid. */
+int ls2fm_grid_points(int32_t n, double step, const double origin[3], int64_t begin, int64_t count, float* xyz, void* stream);
+
 /* ------------------------------------------------------------------ ray generation
  * utils/camera.py:230-252 get_center_and_ray: pose [B,3,4] = [R|t] (world -> camera), kinv [B,3,3] = K^-1, pixel centres
  * xy [N,2] shared by the B cameras -> center [B,N,3] = -R^T t, ray [B,N,3] = R^T K^-1 [x,y,1] (un-normalised).
  * The backward accumulates (+=) the pose gradient d_pose [B,3,4] from g_center / g_ray (nullable each). */
 int ls2fm_generate_rays(const float* pose, const float* kinv, const float* xy, int32_t n_cams, int64_t n_pix,
                         float* center, float* ray, void* stream);
+/* utils/camera.py:85-96,119-142 Lie.se3_to_SE3 with its 11-term Taylor coefficients: wu [n,6] = (w, u) -> Rt [n,3,4] = [R | V u];
+ * one launch instead of ~150 eager ones (BA evaluates it once per tracked POINT per iteration, pipelines/BA.py:127).
+ * backward: d_wu [n,6] (written) = J^T g_Rt. */
+int ls2fm_se3_to_SE3(const float* wu, int64_t n, float* Rt, void* stream);
+int ls2fm_se3_to_SE3_backward(const float* wu, int64_t n, const float* g_Rt, float* d_wu, void* stream);
 int ls2fm_generate_rays_backward(const float* pose, const float* kinv, const float* xy, int32_t n_cams, int64_t n_pix,
                                  const float* g_center, const float* g_ray, float* d_pose, void* stream);
 

@@ -95,9 +95,13 @@ SIGNATURES = {
     "ls2fm_composite_backward": (C.c_int, [_VP] * 6 + [C.c_float, _F3, C.c_int32, C.c_int32] + [_VP] * 10),
     "ls2fm_sample_uniform": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _F3, _F3, _VP, _VP, _VP]),
     "ls2fm_sampler_workspace_bytes": (C.c_int64, [C.POINTER(SamplerCfg), C.c_int32]),
+    "ls2fm_render_tail": (C.c_int, [_VP] * 6 + [C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float] + [_VP] * 8),
+    "ls2fm_grid_points": (C.c_int, [C.c_int32, C.c_double, C.c_double * 3, C.c_int64, C.c_int64, _VP, _VP]),
     "ls2fm_render_loss": (C.c_int, [_VP, _VP, C.c_int64, _VP, C.c_int64, C.c_float, C.c_float, _VP, _VP, _VP, _VP]),
     "ls2fm_generate_rays": (C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_int64, _VP, _VP, _VP]),
     "ls2fm_generate_rays_backward": (C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_int64, _VP, _VP, _VP, _VP]),
+    "ls2fm_se3_to_SE3": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
+    "ls2fm_se3_to_SE3_backward": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP]),
     "ls2fm_sphere_trace": (C.c_int, [C.POINTER(Field), _VP, _VP, C.c_int64, C.c_float, C.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_sample_error_bounded": (C.c_int, [C.POINTER(Field), _VP, C.POINTER(SamplerCfg), _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP]),
 }

@@ -15,6 +15,7 @@
 #include "ls2fm_sampler.cuh"
 #include "ls2fm_trace.cuh"
 #include "ls2fm_params.cuh"
+#include "ls2fm_pose.cuh"
 
 static thread_local std::string g_err;
 
@@ -394,6 +395,7 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
     a.g_y = g_y; a.g_sdf = g_sdf; a.g_nrm = g_nrm; a.g_rgb = g_rgb;
     a.saved_nrm = saved_nrm; a.saved_rgb = saved_rgb;
     a.d_table = d_table; a.d_theta = d_theta; a.d_w_eff = d_w_eff; a.d_b_eff = d_b_eff; a.d_geo2 = d_geo2;
+    if (d_table && (reinterpret_cast<uintptr_t>(d_table) & 7)) return ls_fail("field_backward: d_table must be 8-byte aligned (vector atomics)");
     if (in_grads) a.ig = *in_grads;
     const bool want_dx = a.ig.d_xyz || a.ig.d_center || a.ig.d_ray || a.ig.d_t;
     if (pts->xyz && (a.ig.d_center || a.ig.d_t)) return ls_fail("field_backward: d_center / d_t need ray mode (points.xyz == NULL)");
@@ -603,6 +605,15 @@ int ls2fm_sphere_trace(const ls2fm_field_t* sdf_field, const float* ray0, const 
     return ls_check_launch("sphere_trace");
 }
 
+int ls2fm_grid_points(int32_t n, double step, const double origin[3], int64_t begin, int64_t count, float* xyz, void* stream) {
+    if (n < 2 || count < 0 || begin < 0 || begin + count > (int64_t)n * n * n) return ls_fail("grid_points: bad range");
+    if (count > 0 && (!xyz || !origin)) return ls_fail("grid_points: NULL argument");
+    if (count == 0) return 0;
+    const int bs = 256;
+    LS_LAUNCH(ls_grid_points_kernel, (unsigned)((count + bs - 1) / bs), bs, 0, stream, n, step, origin[0], origin[1], origin[2], begin, count, xyz);
+    return ls_check_launch("grid_points");
+}
+
 int ls2fm_render_loss(const float* rgb, const float* gt, int64_t n_rays, const float* normals, int64_t n_samples, float w_rgb,
                       float w_eik, float* sums, float* g_rgb, float* g_normals, void* stream) {
     if (n_rays < 0 || n_samples < 0 || !sums) return ls_fail("render_loss: bad arguments");
@@ -616,6 +627,46 @@ int ls2fm_render_loss(const float* rgb, const float* gt, int64_t n_rays, const f
     LS_LAUNCH(ls_render_loss_kernel, (unsigned)grid, bs, 0, stream, rgb, gt, 3 * n_rays, normals, n_samples, w_rgb, w_eik, sums, g_rgb,
               g_normals);
     return ls_check_launch("render_loss");
+}
+
+int ls2fm_render_tail(const float* rgb, const float* gt, const float* depth_mlp, const float* d_points, const uint8_t* mask_finish_in,
+                      const float* normals, int64_t n_rays, int32_t n_per_ray, int32_t eik_masked, float w_rgb, float w_eik, float w_dc,
+                      float* sums, uint8_t* mask_bg, uint8_t* mask_finish, float* g_rgb, float* g_depth, float* g_dpoints, float* g_normals,
+                      void* stream) {
+    if (n_rays < 0 || n_per_ray < 0 || !sums) return ls_fail("render_tail: bad arguments");
+    if (n_rays > 0 && (!rgb || !gt || !mask_bg || !mask_finish)) return ls_fail("render_tail: rgb / gt / mask outputs are required");
+    if ((depth_mlp == nullptr) != (d_points == nullptr)) return ls_fail("render_tail: depth_mlp and d_points go together");
+    if (normals && n_per_ray < 1) return ls_fail("render_tail: n_per_ray must be >= 1 with normals");
+    ls_memset_async(sums, 0, 8 * sizeof(float), stream);
+    if (n_rays == 0) return 0;
+    const int bs = 256;
+    int64_t grid = (n_rays + bs - 1) / bs;
+    if (grid > 4 * ls_sm_count()) grid = 4 * ls_sm_count();
+    LS_LAUNCH(ls_render_tail_rays_kernel, (unsigned)grid, bs, 0, stream, rgb, gt, depth_mlp, d_points, mask_finish_in, n_rays, w_rgb, sums,
+              mask_bg, mask_finish, g_rgb);
+    if (ls_check_launch("render_tail(rays)")) return 1;
+    const int64_t work = normals ? n_rays * n_per_ray : n_rays;
+    grid = (work + bs - 1) / bs;
+    if (grid > 8 * ls_sm_count()) grid = 8 * ls_sm_count();
+    LS_LAUNCH(ls_render_tail_grads_kernel, (unsigned)grid, bs, 0, stream, normals, n_rays, n_per_ray, eik_masked, depth_mlp, d_points, mask_bg,
+              mask_finish, w_eik, w_dc, sums, g_normals, g_depth, g_dpoints);
+    return ls_check_launch("render_tail(grads)");
+}
+
+int ls2fm_se3_to_SE3(const float* wu, int64_t n, float* Rt, void* stream) {
+    if (n < 0 || (n > 0 && (!wu || !Rt))) return ls_fail("se3_to_SE3: bad arguments");
+    if (n == 0) return 0;
+    const int bs = 128;
+    LS_LAUNCH(ls_se3_to_SE3_kernel, (unsigned)((n + bs - 1) / bs), bs, 0, stream, wu, n, Rt);
+    return ls_check_launch("se3_to_SE3");
+}
+
+int ls2fm_se3_to_SE3_backward(const float* wu, int64_t n, const float* g_Rt, float* d_wu, void* stream) {
+    if (n < 0 || (n > 0 && (!wu || !g_Rt || !d_wu))) return ls_fail("se3_to_SE3_backward: bad arguments");
+    if (n == 0) return 0;
+    const int bs = 128;
+    LS_LAUNCH(ls_se3_to_SE3_backward_kernel, (unsigned)((n + bs - 1) / bs), bs, 0, stream, wu, n, g_Rt, d_wu);
+    return ls_check_launch("se3_to_SE3_backward");
 }
 
 int ls2fm_generate_rays(const float* pose, const float* kinv, const float* xy, int32_t n_cams, int64_t n_pix, float* center, float* ray,

@@ -51,6 +51,8 @@ LS_DEV float ls_fadd(float a, float b) { return __fadd_rn(a, b); }
 LS_DEV float ls_fsub(float a, float b) { return __fsub_rn(a, b); }
 LS_DEV float ls_fdiv(float a, float b) { return __fdiv_rn(a, b); }
 LS_DEV float ls_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+LS_DEV double ls_dmul(double a, double b) { return __dmul_rn(a, b); }
+LS_DEV double ls_dadd(double a, double b) { return __dadd_rn(a, b); }
 
 // ---------------------------------------------------------------- softplus (beta, threshold)
 // torch.nn.Softplus(beta=100, threshold=20) as the reference's Geometry MLP uses it (models/base.py:203).

@@ -301,6 +301,28 @@ __global__ void ls_grid_encode_backward_kernel(const ls2fm_field_t f, const floa
     }
 }
 
+// ---------------------------------------------------------------- marching-cubes query grid
+// The N^3 query points of utils/util.py:392-411 (extract_mesh), generated on the device instead of in numpy + one H2D copy per
+// 16 k chunk.  Reproduces the reference's float64 arithmetic term by term -- including its true division: the y / x grid
+// coordinates are (idx / N) mod N and ((idx / N) / N) mod N as FLOATS, i.e. slightly sheared, not integer indices:
+//   c2 = idx % N,  c1 = fmod(idx / N, N),  c0 = fmod((idx / N) / N, N);   xyz = (c0, c1, c2) * step + (origin[0], origin[1], origin[2])
+// (the caller passes origin already in the reference's swapped order, util.py:408-410), then a cast to float32.
+__global__ void ls_grid_points_kernel(int N, double step, double o0, double o1, double o2, int64_t begin, int64_t count,
+                                      float* __restrict__ xyz) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int64_t idx = begin + k;
+    const double dn = (double)N;
+    const double c2 = (double)(idx % N);
+    const double q1 = (double)idx / dn;
+    const double c1 = fmod(q1, dn);
+    const double c0 = fmod(q1 / dn, dn);
+    // numpy rounds the product and the sum separately: no fused multiply-add here
+    xyz[3 * k] = (float)ls_dadd(ls_dmul(c0, step), o0);
+    xyz[3 * k + 1] = (float)ls_dadd(ls_dmul(c1, step), o1);
+    xyz[3 * k + 2] = (float)ls_dadd(ls_dmul(c2, step), o2);
+}
+
 // ---------------------------------------------------------------- rendering-loss tail
 // loss = w_rgb * mean|rgb - gt| + w_eik * mean| ||n|| - 1 |   (pipelines/rendering_refine.py:99-121, BA.py:190-204)
 // One pass over rgb [R,3] / gt [R,3] and the per-sample normals [S,3]: partial sums by warp shuffle + one atomic per
@@ -332,6 +354,91 @@ __global__ void ls_render_loss_kernel(const float* __restrict__ rgb, const float
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(sums, s_rgb);
         atomicAdd(sums + 1, s_eik);
+    }
+}
+
+// ---------------------------------------------------------------- full loss tail of CameraSet.render + stage compute_loss
+// pipelines/Camera.py:506-537 + BA.py:190-204 / rendering_refine.py:99-107, two launches for ~25 eager kernels:
+//   mask_bg     = 0.05 < mean(gt) < 0.95                       per ray            (Camera.py:515)
+//   mask_finish = mask_finish(sphere tracing) & mask_bg        per ray            (Camera.py:516)
+//   rgb_loss    = mean |rgb - gt|                              over R * 3         (Camera.py:535)
+//   PSNR        = -10 log10 mean (rgb - gt)^2 over mask_bg rays                   (Camera.py:533)
+//   DC_loss     = mean smooth_l1(d_points - depth_mlp) over mask_finish rays, 0 when there is none   (Camera.py:521-523,531)
+//   eikonal     = mean | ||n|| - 1 | over the samples of mask_bg rays (BA.py:192-193) or over all samples (refine / init)
+// Pass 1 (one thread per ray): masks, the per-ray sums and counts, and g_rgb (its denominator 3R is a constant).
+// sums: [0] sum|rgb-gt|  [1] eikonal sum  [2] #mask_bg  [3] sum (rgb-gt)^2 over mask_bg  [4] smooth-l1 sum  [5] #mask_finish
+__global__ void ls_render_tail_rays_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, const float* __restrict__ depth,
+                                           const float* __restrict__ d_points, const unsigned char* __restrict__ finish_in, int64_t n_rays,
+                                           float w_rgb, float* __restrict__ sums, unsigned char* __restrict__ mask_bg,
+                                           unsigned char* __restrict__ mask_finish, float* __restrict__ g_rgb) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    float s_l1 = 0.f, s_se = 0.f, s_dc = 0.f, n_bg = 0.f, n_fin = 0.f;
+    for (int64_t r = gid; r < n_rays; r += stride) {
+        const float g0 = gt[3 * r], g1 = gt[3 * r + 1], g2 = gt[3 * r + 2];
+        const float m = ((g0 + g1) + g2) / 3.f;
+        const bool bg = m < 0.95f && m > 0.05f;
+        const bool fin = bg && finish_in && finish_in[r] != 0;
+        if (mask_bg) mask_bg[r] = bg ? 1 : 0;
+        if (mask_finish) mask_finish[r] = fin ? 1 : 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float d = rgb[3 * r + c] - gt[3 * r + c];
+            s_l1 += fabsf(d);
+            if (bg) s_se += d * d;
+            if (g_rgb) g_rgb[3 * r + c] = (d > 0.f ? w_rgb : (d < 0.f ? -w_rgb : 0.f)) / (float)(3 * n_rays);
+        }
+        if (bg) n_bg += 1.f;
+        if (fin && depth && d_points) {
+            const float d = d_points[r] - depth[r], ad = fabsf(d);
+            s_dc += ad < 1.f ? 0.5f * d * d : ad - 0.5f;
+            n_fin += 1.f;
+        }
+    }
+    s_l1 = ls_warp_sum(s_l1); s_se = ls_warp_sum(s_se); s_dc = ls_warp_sum(s_dc); n_bg = ls_warp_sum(n_bg); n_fin = ls_warp_sum(n_fin);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sums, s_l1); atomicAdd(sums + 2, n_bg); atomicAdd(sums + 3, s_se); atomicAdd(sums + 4, s_dc); atomicAdd(sums + 5, n_fin);
+    }
+}
+// Pass 2: the terms whose mean runs over a data-dependent count (read from sums, written by pass 1): the eikonal sum and its
+// gradient over the per-sample normals, and the depth-consistency gradients (+d to d_points, -d to depth_mlp).
+__global__ void ls_render_tail_grads_kernel(const float* __restrict__ nrm, int64_t n_rays, int n_per_ray, int eik_masked,
+                                            const float* __restrict__ depth, const float* __restrict__ d_points,
+                                            const unsigned char* __restrict__ mask_bg, const unsigned char* __restrict__ mask_finish,
+                                            float w_eik, float w_dc, float* __restrict__ sums, float* __restrict__ g_nrm,
+                                            float* __restrict__ g_depth, float* __restrict__ g_dpoints) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float n_bg = sums[2], n_fin = sums[5];
+    const int64_t n_samples = n_rays * n_per_ray;
+    const float cnt_eik = eik_masked ? n_bg * (float)n_per_ray : (float)n_samples;
+    float s_eik = 0.f;
+    if (nrm) {
+        for (int64_t i = gid; i < n_samples; i += stride) {
+            const bool on = !eik_masked || mask_bg[i / n_per_ray] != 0;
+            float k = 0.f, x = 0.f, y = 0.f, z = 0.f;
+            if (on) {
+                x = nrm[3 * i]; y = nrm[3 * i + 1]; z = nrm[3 * i + 2];
+                const float len = sqrtf(x * x + y * y + z * z);
+                const float e = len - 1.f;
+                s_eik += fabsf(e);
+                k = (len > 0.f && cnt_eik > 0.f) ? (e > 0.f ? w_eik : (e < 0.f ? -w_eik : 0.f)) / (len * cnt_eik) : 0.f;
+            }
+            if (g_nrm) { g_nrm[3 * i] = k * x; g_nrm[3 * i + 1] = k * y; g_nrm[3 * i + 2] = k * z; }
+        }
+        s_eik = ls_warp_sum(s_eik);
+        if ((threadIdx.x & 31) == 0) atomicAdd(sums + 1, s_eik);
+    }
+    if (depth && d_points && (g_depth || g_dpoints)) {
+        for (int64_t r = gid; r < n_rays; r += stride) {
+            float g = 0.f;
+            if (mask_finish[r] && n_fin > 0.f) {
+                const float d = d_points[r] - depth[r];
+                g = w_dc * fminf(fmaxf(d, -1.f), 1.f) / n_fin;
+            }
+            if (g_dpoints) g_dpoints[r] = g;
+            if (g_depth) g_depth[r] = -g;
+        }
     }
 }
 

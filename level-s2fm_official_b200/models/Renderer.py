@@ -107,6 +107,54 @@ class Renderer:
         return {"rgb": rgb.view(B, R, 3), "sdfs_volume": sdf.view(B, R, N, 1), "normals": nrm.view(B, R, N, 3),
                 "depth_mlp": depth.view(B, R, 1), "normal_mlp": normal.view(B, R, 3)}
 
+    @torch.no_grad()
+    def render_image(self, opt, center, ray, SDF_Field, Rad_Field, slice_rays=None):
+        """No-grad rendering of MANY rays (a whole image) in slices: what ``Camera.render_img_by_slices`` does with one
+        ``Renderer.forward`` per ``opt.Renderer.rand_rays`` rays (pipelines/Camera.py:275-311), returning its dict
+        ``depth [B,HW,1]``, ``norm [B,HW,3]``, ``rgb [B,HW,3]``.  Differences from calling ``forward`` per slice: the effective
+        weights and their tensor-core operand image are built once for the whole image, nothing per-sample survives a slice,
+        no autograd tape."""
+        if SDF_Field._bg_sdf():
+            raise NotImplementedError("opt.data.bg_sdf is not fused into the render kernels")
+        lib = _C.get()
+        B, HW = center.shape[:2]
+        n_slice = int(slice_rays or opt.Renderer.rand_rays)
+        prepared = self._prepare(SDF_Field, Rad_Field)
+        theta = prepared["theta"].detach().contiguous()
+        w_eff, b_eff = prepared["w_eff"].detach().contiguous(), prepared["b_eff"].detach().contiguous()
+        spec, rs = SDF_Field.field_spec(), Rad_Field.rad_spec()
+        table = SDF_Field.table().detach()
+        dual = Rad_Field.dual_field
+        if dual:
+            spec2, table2 = Rad_Field.field_spec(), Rad_Field.embed_fn.embedder_obj.params.detach()
+            theta2 = Rad_Field.Geo_enc.theta().detach().contiguous()
+            image2 = ops.field_prepare_raw(lib, spec2, table2, theta2, None)
+        dev = table.device
+        depth = torch.empty(B, HW, 1, device=dev)
+        norm = torch.empty(B, HW, 3, device=dev)
+        rgb = torch.empty(B, HW, 3, device=dev)
+        for start in range(0, HW, n_slice):
+            end = min(start + n_slice, HW)
+            c2 = center[:, start:end].reshape(-1, 3).float().contiguous()
+            r2 = ray[:, start:end].reshape(-1, 3).float().contiguous()
+            t, _, _ = self.volsdf_sampling(opt, c2[None], r2[None], SDF_Field, prepared=prepared)
+            t2 = t.reshape(c2.shape[0], -1).contiguous()
+            geo2 = None
+            if dual:
+                pts2 = ops._points(lib, None, c2, r2, t2)
+                geo2, _, _, _ = ops.field_forward_raw(lib, spec2, table2, theta2, pts2, None, want_y=True, want_sdf=False, image=image2)
+            pts = ops._points(lib, None, c2, r2, t2)
+            rad = ops._rad(lib, rs, w_eff, b_eff, geo2)
+            _, sdf, nrm, rgbs = ops.field_forward_raw(lib, spec, table, theta, pts, rad, want_nrm=True, want_rgb=True,
+                                                      image=prepared["image"])
+            N = t2.shape[-1]
+            o_rgb, o_depth, o_nrm, _ = ops.composite_forward_raw(lib, r2, t2, sdf.view(-1, N), rgbs.view(-1, N, 3), nrm.view(-1, N, 3),
+                                                                 SDF_Field.beta.detach(), float(SDF_Field.beta_speed), self._bg)
+            depth[:, start:end] = o_depth.view(B, end - start, 1)
+            norm[:, start:end] = o_nrm.view(B, end - start, 3)
+            rgb[:, start:end] = o_rgb.view(B, end - start, 3)
+        return {"depth": depth, "norm": norm, "rgb": rgb}
+
     render_rays = forward    # north-star alias
 
     # ------------------------------------------------------------------ API-compatible pieces

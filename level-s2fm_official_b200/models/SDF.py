@@ -116,6 +116,37 @@ class SDF(nn.Module):
         surf_pts = pts - normals / normals_value.detach() * sdf
         return surf_pts, normals_value
 
+    @torch.no_grad()
+    def infer_sdf_grid(self, N=512, volume_size=2.0, bound_max=None, bound_min=None, chunk=1 << 22):
+        """The [N,N,N] SDF volume the reference's marching-cubes export evaluates (utils/util.py:392-430 ``extract_mesh``:
+        N^3 numpy points, ``infer_sdf`` in 16 k chunks through host memory, reshape) -- generated and evaluated on the device
+        in ``chunk``-point launches of the values-only tensor-core kernel; nothing but the N^3 floats ever leaves the GPU.
+        Same point arithmetic as the reference (float64, its true-division quirk included), so
+        ``infer_sdf_grid(N, s, bmax, bmin)`` == ``extract_mesh``'s ``out`` array."""
+        from .. import _C
+        lib = _C.get()
+        s = float(volume_size)
+        origin = [-s / 2.0] * 3
+        if bound_max is not None:
+            origin = [float(v) for v in bound_min]
+        step = s / (N - 1)
+        org = (origin[2], origin[1], origin[0])            # util.py:408-410 adds origin[2] to x, origin[0] to z
+        dev = self.table().device
+        spec, table = self.field_spec(), self.table().detach()
+        theta = self.SDF_MLP.theta().detach().contiguous()
+        image = ops.field_prepare_raw(lib, spec, table, theta, None)
+        total = N ** 3
+        out = torch.empty(total, device=dev)
+        for begin in range(0, total, chunk):
+            cnt = min(chunk, total - begin)
+            xyz = ops.grid_points_raw(lib, N, step, org, begin, cnt, dev)
+            pts = ops._points(lib, xyz, None, None, None)
+            _, sdf, _, _ = ops.field_forward_raw(lib, spec, table, theta, pts, None, image=image)
+            if self._bg_sdf():
+                sdf = torch.min(sdf, self.opt.data.bg_rad - xyz.norm(dim=-1))
+            out[begin:begin + cnt] = sdf
+        return out.view(N, N, N)
+
     def sphere_tracing(self, ray0, ray_direction, model=None, c=None, tau=0.5, n_steps=(128, 129), n_secant_steps=8,
                        depth_range=(0.0, 2.4), max_points=3500000, rad=1.0, iter=0):
         """Bidirectional sphere tracing (models/SDF.py:116-226).  Returns (d_pred [B,M] differentiable w.r.t. the
@@ -133,6 +164,16 @@ class SDF(nn.Module):
         acc_e = acc_hist[n_it]
         pts_tracks = track[:, :max(n_it, 1)]                                # [M,K,3]; K = 0 keeps the start point
         sdf_tracks = self.infer_sdf(pts_tracks)                          # [M,K,1], with grad
+        if torch.is_grad_enabled() and (ray0.requires_grad or ray_direction.requires_grad):
+            # d_pred = sum sdf(track points, constants) + t_near, clamped to t_far: the rays enter through the slab test only
+            # (models/SDF.py:120-123,204-205).  The reference's RayAABBIntersector has no backward; ours has (SURVEY 8a defect
+            # iii) unless opt.Renderer.aabb_grad is False.
+            if getattr(getattr(self.opt, "Renderer", None), "aabb_grad", True) == False:   # noqa: E712
+                raise NotImplementedError("RayAABBIntersector has no backward in the reference (utils/custom_functions.py:10-31); "
+                                          "set opt.Renderer.aabb_grad = True for the analytic slab-test gradient")
+            hits = ops.RayAABB.apply(ray0.reshape(-1, 3), ray_direction.reshape(-1, 3), [float(x) for x in self.opt.data.bound_min],
+                                     [float(x) for x in self.opt.data.bound_max])
+            t_near, t_far = hits[:, 0], hits[:, 1]
         d_pred = sdf_tracks.sum(dim=-2).view(*ray0.shape[:-1]) + t_near.view(*ray0.shape[:-1])
         d_pred = torch.minimum(d_pred, t_far.view(*d_pred.shape))
         thr2 = float(self.opt.data.bound_max[0] - self.opt.data.bound_min[0]) / 10 / self.opt.Res
@@ -142,7 +183,7 @@ class SDF(nn.Module):
         factor_rand = torch.rand_like(d_pred)
         d_up = torch.minimum(1.5 * acc_e.view(*d_pred.shape), tf_v)
         d_sample = (1 - factor_rand) * d_up + factor_rand * tn_v
-        sampled_pts = ray0.detach() + d_sample[..., None].detach() * ray_direction.detach()
+        sampled_pts = ray0 + d_sample[..., None] * ray_direction          # (callers detach it, e.g. pipelines/Camera.py:243)
         pick = torch.randperm(pts_tracks.shape[0], device=pts_tracks.device)[:4096]
         sampled_pts = torch.cat([pts_tracks[pick].view(1, -1, 3), sampled_pts.view(1, -1, 3)], dim=1)
         return d_pred, sdf_tracks[:, -1, 0], sampled_pts, finish_mask

@@ -124,12 +124,13 @@ def compose_affine(layers: List[Tuple[torch.Tensor, torch.Tensor]]) -> Tuple[tor
 # ------------------------------------------------------------------------- launch log
 class KernelLog:
     """Counts the launches of our kernels and, when ``timing`` is on, brackets each launch with CUDA events on the
-    launching stream (used by bench.py for ``gpu_launches`` and the roofline of the dominant kernel)."""
+    launching stream (used by bench.py for ``gpu_launches`` and the roofline of the dominant kernel).  ``units`` = the
+    samples / rays that launch processes, so per-launch algorithmic bytes can be attached to per-launch durations."""
 
     def __init__(self):
         self.counts = {}
         self.timing = False
-        self.events = []        # (name, start, end)
+        self.events = []        # (name, start, end, units)
 
     def reset(self):
         self.counts = {}
@@ -146,27 +147,31 @@ class KernelLog:
             return ev
         return None
 
-    def end(self, name, start):
+    def end(self, name, start, units=None):
         if start is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
-            self.events.append((name, start, ev))
+            self.events.append((name, start, ev, units))
 
     def durations_ms(self):
         """name -> list of per-launch durations (call after torch.cuda.synchronize())."""
         out = {}
-        for name, a, b in self.events:
+        for name, a, b, _ in self.events:
             out.setdefault(name, []).append(a.elapsed_time(b))
         return out
+
+    def launches(self):
+        """[(name, ms, units)] in launch order (call after torch.cuda.synchronize())."""
+        return [(name, a.elapsed_time(b), units) for name, a, b, units in self.events]
 
 
 KLOG = KernelLog()
 
 
-def _call(lib, name, fn, *args, launches=1):
+def _call(lib, name, fn, *args, launches=1, units=None):
     ev = KLOG.begin(name, launches)
     lib.check(fn(*args))
-    KLOG.end(name, ev)
+    KLOG.end(name, ev, units)
 
 
 # ------------------------------------------------------------------------- raw calls
@@ -220,7 +225,7 @@ def field_forward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: O
     if FORWARD_WS and rad is None and not want_nrm and not want_rgb and not simt:      # experimental warp-specialised kernel (tests only)
         _call(lib, "field_forward_ws", lib.dll.ls2fm_field_forward_ws, f, pts, lib.ptr(y), lib.ptr(sdf), lib.stream())
         return y, sdf, nrm, rgb
-    _call(lib, "field_forward_simt" if simt else "field_forward", lib.dll.ls2fm_field_forward_simt if simt else lib.dll.ls2fm_field_forward, f, pts, rad, lib.ptr(y), lib.ptr(sdf), lib.ptr(nrm), lib.ptr(rgb), lib.stream())
+    _call(lib, "field_forward_simt" if simt else "field_forward", lib.dll.ls2fm_field_forward_simt if simt else lib.dll.ls2fm_field_forward, f, pts, rad, lib.ptr(y), lib.ptr(sdf), lib.ptr(nrm), lib.ptr(rgb), lib.stream(), units=n)
     return y, sdf, nrm, rgb
 
 
@@ -242,7 +247,7 @@ def field_backward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: 
         mode = "auto"       # no operand image / no gradient on the normals: nothing for the tensor-core kernel to do
     name = {"auto": "field_backward", "simt": "field_backward_simt", "tc": "field_backward_tc"}[mode]
     _call(lib, name, getattr(lib.dll, "ls2fm_" + name), f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
-        lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), ig, lib.stream())
+        lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), ig, lib.stream(), units=int(pts.n))
 
 
 def grid_encode_raw(lib, grid: GridSpec, table, u, want_idx=False):
@@ -324,7 +329,8 @@ def grad_sink(param):
     instead of a fresh zero-filled 49 MB tensor that autograd adds to ``.grad`` afterwards (two extra passes over the table
     per backward).  Not valid under ``torch.autograd.grad`` -- which is why it is opt-in."""
     sink = getattr(param, "_ls2fm_grad_sink", None)
-    if sink is not None and (sink.shape != param.shape or sink.device != param.device or not sink.is_contiguous()):
+    if sink is not None and (sink.shape != param.shape or sink.device != param.device or not sink.is_contiguous()
+                             or sink.data_ptr() % 8 or sink.dtype != torch.float32):
         return None
     return sink
 
@@ -456,10 +462,52 @@ class Composite(torch.autograd.Function):
         return d_ray, d_t, d_sdf, d_rgbs, d_nrm, d_beta.view_as(beta_param), None, None
 
 
+def _aabb_vjp(c, r, hits, g_near, g_far, bmin, bmax):
+    """VJP of the slab test the reference's RayAABBIntersector lacks (utils/custom_functions.py:10-31; SURVEY 8a defect iii):
+    on the slab axis k that decides t_near / t_far,  dt/do_k = -1/d_k,  dt/dd_k = -t/d_k;  zero where t_near was clamped to 0 or
+    the ray misses the box.  c, r [M,3]; hits [M,2]; g_near, g_far [M] -> (d_c, d_r)."""
+    lo_p = torch.tensor(bmin, device=c.device, dtype=c.dtype)
+    hi_p = torch.tensor(bmax, device=c.device, dtype=c.dtype)
+    inv = 1.0 / r
+    t_lo, t_hi = (lo_p - c) * inv, (hi_p - c) * inv
+    k_near = torch.minimum(t_lo, t_hi).argmax(dim=-1, keepdim=True)
+    k_far = torch.maximum(t_lo, t_hi).argmin(dim=-1, keepdim=True)
+    hit = hits[:, 1] > 0
+    g_near = torch.where(hit & (hits[:, 0] > 0), g_near, torch.zeros_like(g_near))
+    g_far = torch.where(hit, g_far, torch.zeros_like(g_far))
+    d_c, d_r = torch.zeros_like(c), torch.zeros_like(r)
+    for k, g, tv in ((k_near, g_near, hits[:, 0]), (k_far, g_far, hits[:, 1])):
+        inv_k = inv.gather(-1, k)[:, 0]
+        d_c.scatter_add_(-1, k, (-g * inv_k)[:, None])
+        d_r.scatter_add_(-1, k, (-g * tv * inv_k)[:, None])
+    return d_c, d_r
+
+
+class RayAABB(torch.autograd.Function):
+    """``RayAABBIntersector.apply`` for one box with the analytic backward: forward(rays_o [M,3], rays_d [M,3], bound_min, bound_max)
+    -> hits_t [M,2] = (t_near, t_far) or (-1, -1)."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, bound_min, bound_max):
+        lib = _C.get()
+        o, d = _c(rays_o.detach().float()), _c(rays_d.detach().float())
+        center = [(float(a) + float(b)) / 2 for a, b in zip(bound_min, bound_max)]
+        half = [(float(b) - float(a)) / 2 for a, b in zip(bound_min, bound_max)]
+        hits, _ = ray_aabb_raw(lib, o, d, center, half)
+        ctx.save_for_backward(o, d, hits)
+        ctx.misc = (tuple(float(x) for x in bound_min), tuple(float(x) for x in bound_max))
+        return hits
+
+    @staticmethod
+    def backward(ctx, g_hits):
+        o, d, hits = ctx.saved_tensors
+        d_o, d_d = _aabb_vjp(o, d, hits, g_hits[:, 0], g_hits[:, 1], *ctx.misc)
+        return d_o, d_d, None, None
+
+
 class UniformDepths(torch.autograd.Function):
     """Ray / AABB slab test + Renderer.sample_depth (models/Renderer.py:118-127,178-185) as ONE launch, with the analytic VJP the
-    reference's RayAABBIntersector lacks (utils/custom_functions.py:10-31; SURVEY 8a defect iii): on the slab axis that decides
-    t_near / t_far, dt/do_k = -1/d_k and dt/dd_k = -t/d_k; zero where t_near was clamped to 0 or the ray misses the box.
+    reference's RayAABBIntersector lacks (``_aabb_vjp``).
 
     forward(center [R,3], ray [R,3], n_samples, bound_min, bound_max) -> t [R,N]"""
 
@@ -479,20 +527,7 @@ class UniformDepths(torch.autograd.Function):
         frac = (torch.arange(n, device=g_t.device, dtype=g_t.dtype) + 0.5) / n
         g_far = (g_t * frac).sum(-1)
         g_near = g_t.sum(-1) - g_far
-        lo_p = torch.tensor(bmin, device=c.device, dtype=c.dtype)
-        hi_p = torch.tensor(bmax, device=c.device, dtype=c.dtype)
-        inv = 1.0 / r
-        t_lo, t_hi = (lo_p - c) * inv, (hi_p - c) * inv
-        k_near = torch.minimum(t_lo, t_hi).argmax(dim=-1, keepdim=True)
-        k_far = torch.maximum(t_lo, t_hi).argmin(dim=-1, keepdim=True)
-        hit = hits[:, 1] > 0
-        g_near = torch.where(hit & (hits[:, 0] > 0), g_near, torch.zeros_like(g_near))
-        g_far = torch.where(hit, g_far, torch.zeros_like(g_far))
-        d_c, d_r = torch.zeros_like(c), torch.zeros_like(r)
-        for k, g, tv in ((k_near, g_near, hits[:, 0]), (k_far, g_far, hits[:, 1])):
-            inv_k = inv.gather(-1, k)[:, 0]
-            d_c.scatter_add_(-1, k, (-g * inv_k)[:, None])
-            d_r.scatter_add_(-1, k, (-g * tv * inv_k)[:, None])
+        d_c, d_r = _aabb_vjp(c, r, hits, g_near, g_far, bmin, bmax)
         return d_c, d_r, None, None, None
 
 
@@ -553,6 +588,14 @@ def sphere_trace_raw(lib, spec: FieldSpec, table, theta, ray0, ray_dir, sdf_thre
     return track, cnt, t_near, t_far, acc_end
 
 
+def grid_points_raw(lib, n, step, origin, begin, count, device):
+    """utils/util.py:392-411 query points [count,3] for flat grid indices [begin, begin+count) (float64 arithmetic on the device)."""
+    xyz = torch.empty(count, 3, device=device)
+    o = (_C.C.c_double * 3)(float(origin[0]), float(origin[1]), float(origin[2]))
+    _call(lib, "grid_points", lib.dll.ls2fm_grid_points, int(n), float(step), o, int(begin), int(count), lib.ptr(xyz), lib.stream())
+    return xyz
+
+
 class RenderLoss(torch.autograd.Function):
     """w_rgb * mean|rgb - gt| + w_eik * mean| ||normals|| - 1 | in one kernel (forward value and both gradients in the
     same pass); the rendering-loss tail of pipelines/rendering_refine.py:99-121 / BA.py:190-204.
@@ -579,6 +622,61 @@ class RenderLoss(torch.autograd.Function):
     def backward(ctx, g_out, _g1, _g2):
         g_rgb, g_nrm = ctx.saved_tensors
         return g_rgb * g_out, None, g_nrm * g_out, None, None
+
+
+class RenderTail(torch.autograd.Function):
+    """The loss tail of ``CameraSet.render`` + the stage's ``compute_loss`` (pipelines/Camera.py:506-537, BA.py:190-204,
+    rendering_refine.py:99-107) in two launches: background / finish masks, rgb L1, PSNR, smooth-L1 depth consistency between the
+    sphere-traced and the volume-rendered depth, (masked) eikonal -- values and every gradient in the same passes.
+
+    forward(rgb [...,3], gt [...,3], normals [..., N, 3] | None, depth_mlp [...,1] | None, d_points [...] | None,
+            mask_finish [...] bool | None, w_rgb, w_eik, w_dc, eik_masked)
+        -> (total, rgb_loss, eikonal, DC_loss, PSNR, mask_bg [R] bool, mask_finish [R] bool);  only ``total`` carries gradient:
+           total = w_rgb * rgb_loss + w_eik * eikonal + w_dc * DC_loss."""
+
+    @staticmethod
+    def forward(ctx, rgb, gt, normals, depth_mlp, d_points, mask_finish, w_rgb, w_eik, w_dc, eik_masked):
+        lib = _C.get()
+        dev = rgb.device
+        rgb_c, gt_c = rgb.detach().reshape(-1, 3).contiguous().float(), gt.detach().reshape(-1, 3).contiguous().float()
+        R = rgb_c.shape[0]
+        nrm_c = normals.detach().contiguous().float() if normals is not None else None
+        npr = (nrm_c.numel() // 3) // max(R, 1) if nrm_c is not None else 0
+        dep_c = depth_mlp.detach().reshape(-1).contiguous().float() if depth_mlp is not None else None
+        dpt_c = d_points.detach().reshape(-1).contiguous().float() if d_points is not None else None
+        fin_c = mask_finish.detach().reshape(-1).to(torch.uint8).contiguous() if mask_finish is not None else None
+        sums = torch.empty(8, device=dev)
+        m_bg = torch.empty(R, dtype=torch.uint8, device=dev)
+        m_fin = torch.empty(R, dtype=torch.uint8, device=dev)
+        g_rgb = torch.empty_like(rgb_c)
+        g_nrm = torch.empty_like(nrm_c) if nrm_c is not None else None
+        g_dep = torch.empty_like(dep_c) if dep_c is not None else None
+        g_dpt = torch.empty_like(dpt_c) if dpt_c is not None else None
+        _call(lib, "render_tail", lib.dll.ls2fm_render_tail, lib.ptr(rgb_c), lib.ptr(gt_c), lib.ptr(dep_c), lib.ptr(dpt_c),
+              lib.ptr(fin_c, torch.uint8), lib.ptr(nrm_c), R, int(npr), int(bool(eik_masked)), float(w_rgb), float(w_eik), float(w_dc),
+              lib.ptr(sums), lib.ptr(m_bg, torch.uint8), lib.ptr(m_fin, torch.uint8), lib.ptr(g_rgb), lib.ptr(g_dep), lib.ptr(g_dpt),
+              lib.ptr(g_nrm), lib.stream(), launches=2)
+        ctx.save_for_backward(g_rgb, g_nrm, g_dep, g_dpt)
+        ctx.shapes = (rgb.shape, normals.shape if normals is not None else None, depth_mlp.shape if depth_mlp is not None else None,
+                      d_points.shape if d_points is not None else None)
+        l1 = sums[0] / max(3 * R, 1)
+        cnt_eik = sums[2] * npr if eik_masked else torch.full((), float(max(R * npr, 1)), device=dev)
+        eik = sums[1] / cnt_eik if nrm_c is not None else torch.zeros((), device=dev)
+        dc = torch.where(sums[5] > 0, sums[4] / sums[5].clamp_min(1.0), torch.zeros((), device=dev))
+        psnr = -10.0 * torch.log10(sums[3] / (3.0 * sums[2]))
+        total = w_rgb * l1 + w_eik * eik + w_dc * dc
+        outs = (total, l1, eik, dc, psnr, m_bg.bool(), m_fin.bool())
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_out, *_):
+        g_rgb, g_nrm, g_dep, g_dpt = ctx.saved_tensors
+        s_rgb, s_nrm, s_dep, s_dpt = ctx.shapes
+        return (
+            (g_rgb * g_out).view(s_rgb), None, (g_nrm * g_out).view(s_nrm) if g_nrm is not None else None,
+            (g_dep * g_out).view(s_dep) if g_dep is not None else None, (g_dpt * g_out).view(s_dpt) if g_dpt is not None else None,
+            None, None, None, None, None)
 
 
 def _param_layers(lib, layers, grads=None):
@@ -667,3 +765,27 @@ class GenerateRays(torch.autograd.Function):
         _call(lib, "generate_rays_backward", lib.dll.ls2fm_generate_rays_backward, lib.ptr(pose), lib.ptr(kinv), lib.ptr(xy),
               pose.shape[0], xy.shape[0], lib.ptr(_c(g_center)), lib.ptr(_c(g_ray)), lib.ptr(d_pose), lib.stream())
         return d_pose, None, None
+
+
+class Se3ToSE3(torch.autograd.Function):
+    """utils/camera.py:85-96 (Lie.se3_to_SE3, Taylor coefficients of camera.py:119-142) as one kernel each way:
+    wu [...,6] -> Rt [...,3,4]."""
+
+    @staticmethod
+    def forward(ctx, wu):
+        lib = _C.get()
+        w = wu.detach().reshape(-1, 6).contiguous().float()
+        Rt = torch.empty(w.shape[0], 3, 4, device=w.device)
+        _call(lib, "se3_to_SE3", lib.dll.ls2fm_se3_to_SE3, lib.ptr(w), w.shape[0], lib.ptr(Rt), lib.stream())
+        ctx.save_for_backward(w)
+        ctx.shape = wu.shape
+        return Rt.view(*wu.shape[:-1], 3, 4)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _C.get()
+        (w,) = ctx.saved_tensors
+        d = torch.empty_like(w)
+        _call(lib, "se3_to_SE3_backward", lib.dll.ls2fm_se3_to_SE3_backward, lib.ptr(w), w.shape[0], lib.ptr(g.reshape(-1, 12).contiguous().float()),
+              lib.ptr(d), lib.stream())
+        return d.view(ctx.shape)

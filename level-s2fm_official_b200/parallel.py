@@ -24,11 +24,20 @@ class GradBucket:
     """All parameter gradients as views into one flat fp32 buffer, laid out so the single all-reduce that follows the
     fused backward needs no packing step.  ``extra`` floats at the tail carry loss sums / counts."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 8, symmetric: bool = False):
+    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 8, symmetric: bool = False, direct: bool = True):
+        """direct: the fused backward kernels scatter the hash-table gradients straight into the bucket (``ops.grad_sink``) instead
+        of into a zero-filled temporary that autograd then adds to ``.grad`` -- two passes over the 49 MB table less per backward.
+        Valid for ``loss.backward()`` training loops (the bucket IS ``.grad``); leave it off when calling ``torch.autograd.grad``."""
+        self.direct = direct
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        # every parameter starts on a 16-byte boundary of the bucket: the fused backward scatters into these views with 8-byte vector
+        # atomics (red.global.add.v2.f32), and the multimem reduction moves whole 16-byte words
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
         dev = self.params[0].device
-        extra += (-(total + extra)) % 4          # whole 16-byte words: what the multimem reduction moves
+        extra += (-(total + extra)) % 4
         self.flat = None
         self.group_name = None      # set when the bucket lives in symmetric memory and the NVSwitch can reduce it (NVLS multicast)
         if (symmetric and dev.type == "cuda" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -56,22 +65,22 @@ class GradBucket:
                 self.flat, self.group_name = None, None
         if self.flat is None:
             self.flat = torch.zeros(total + extra, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        self.extra = self.flat[off:]
+            if direct:
+                p._ls2fm_grad_sink = p.grad
+        self.extra = self.flat[total:]
 
     def zero(self):
         self.flat.zero_()
 
     def rebind(self):
         """optimizers / zero_grad(set_to_none=True) may drop the views; call before backward."""
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != self.flat[off:off + p.numel()].data_ptr():
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            if self.direct:
+                p._ls2fm_grad_sink = p.grad
 
     def allreduce(self, async_op: bool = False):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -29,3 +29,8 @@ def get_center_and_ray(opt, pose, intr=None, rays_idx=None, xy_grid=None):
         raise ValueError(f"intr has {kinv.shape[0]} matrices for {len(pose)} cameras")
     kinv = kinv.expand(len(pose), 3, 3).contiguous()
     return ops.GenerateRays.apply(pose, kinv, xy)
+
+
+def se3_to_SE3(wu):
+    """``camera.lie.se3_to_SE3`` (utils/camera.py:85-96): wu [...,6] -> [...,3,4], one kernel, differentiable."""
+    return ops.Se3ToSE3.apply(wu)

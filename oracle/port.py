@@ -415,7 +415,7 @@ def volsdf_sampling(center: Tensor, ray: Tensor, sdf_sd, cfg: SceneCfg):
         if bool(torch.all(max_d == -1)):
             max_d = torch.zeros_like(max_d)
         # the reference computes log(1+eps) in float32 (torch.log of a float32 tensor)
-        beta = torch.sqrt(max_d ** 2 / (4 * (N - 1) * torch.log(1 + torch.tensor([cfg.eps], dtype=tn.dtype))))
+        beta = torch.sqrt(max_d ** 2 / (4 * (N - 1) * torch.log(1 + torch.tensor([cfg.eps], dtype=tn.dtype, device=tn.device))))
         alpha = 1.0 / beta
         d = sample_depth(tn, tf, N)                                              # [R,N]
         pts = c[:, None, :] + r[:, None, :] * d[..., None]
@@ -423,8 +423,8 @@ def volsdf_sampling(center: Tensor, ray: Tensor, sdf_sd, cfg: SceneCfg):
         a_net, b_net = forward_ab(sdf_sd, cfg)
         active = error_bound(d, sdf, a_net, b_net).max(-1).values > cfg.eps       # 'mask'
         bounds = error_bound(d, sdf, alpha[:, None], beta[:, None])
-        fine = torch.zeros(R_, cfg.final_sample_intvs, dtype=tn.dtype)
-        iters = torch.zeros(R_, dtype=tn.dtype)
+        fine = torch.zeros(R_, cfg.final_sample_intvs, dtype=tn.dtype, device=tn.device)
+        iters = torch.zeros(R_, dtype=tn.dtype, device=tn.device)
         conv = ~active
         if conv.any():
             fine[conv] = opacity_to_sample(d[conv], sdf[conv], a_net, b_net, cfg.final_sample_intvs)
@@ -440,9 +440,9 @@ def volsdf_sampling(center: Tensor, ray: Tensor, sdf_sd, cfg: SceneCfg):
             d_sorted, order = torch.sort(d_cat, -1)
             s_sorted = s_cat.gather(-1, order)
             # grow the per-ray storage (inactive rays keep zeros in the tail, never read again)
-            d = torch.cat([d, torch.zeros(R_, N, dtype=d.dtype)], -1)
-            sdf = torch.cat([sdf, torch.zeros(R_, N, dtype=d.dtype)], -1)
-            bounds = torch.cat([bounds, torch.zeros(R_, N, dtype=d.dtype)], -1)
+            d = torch.cat([d, torch.zeros(R_, N, dtype=d.dtype, device=d.device)], -1)
+            sdf = torch.cat([sdf, torch.zeros(R_, N, dtype=d.dtype, device=d.device)], -1)
+            bounds = torch.cat([bounds, torch.zeros(R_, N, dtype=d.dtype, device=d.device)], -1)
             d[idx], sdf[idx] = d_sorted, s_sorted
             still = error_bound(d_sorted, s_sorted, a_net, b_net).max(-1).values > cfg.eps
             done_idx = idx[~still]
@@ -589,3 +589,29 @@ def get_center_and_ray(pose: Tensor, intr: Tensor, xy: Tensor):
     gw = cam2world(grid)
     cw = cam2world(torch.zeros_like(grid))
     return cw, gw - cw
+
+
+def se3_to_SE3(wu: Tensor) -> Tensor:
+    """Lie.se3_to_SE3, utils/camera.py:85-96, with the Taylor coefficients of camera.py:119-142 (nth = 10):
+    wu [...,6] -> Rt [...,3,4] = [I + A wx + B wx^2 | (I + B wx + C wx^2) u]."""
+    w, u = wu.split([3, 3], dim=-1)
+    w0, w1, w2 = w.unbind(dim=-1)
+    O = torch.zeros_like(w0)
+    wx = torch.stack([torch.stack([O, -w2, w1], dim=-1), torch.stack([w2, O, -w0], dim=-1), torch.stack([-w1, w0, O], dim=-1)], dim=-2)
+    theta = w.norm(dim=-1)[..., None, None]
+    eye = torch.eye(3, device=w.device, dtype=torch.float32)
+
+    def taylor(x, first, step):
+        ans, denom = torch.zeros_like(x), 1.0
+        for i in range(11):
+            if first is None:
+                if i > 0:
+                    denom *= (2 * i) * (2 * i + 1)
+            else:
+                denom *= (2 * i + first) * (2 * i + first + 1)
+            ans = ans + (-1) ** i * x ** (2 * i) / denom
+        return ans
+    A, B, C = taylor(theta, None, 0), taylor(theta, 1, 0), taylor(theta, 2, 0)
+    R = eye + A * wx + B * wx @ wx
+    V = eye + B * wx + C * wx @ wx
+    return torch.cat([R, V @ u[..., None]], dim=-1)

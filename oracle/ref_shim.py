@@ -129,6 +129,38 @@ def load():
     return _loaded
 
 
+_pipelines = None
+
+
+def load_pipelines():
+    """The reference's UNMODIFIED pipelines/Camera.py, BA.py, Point3D.py (callers of the hot path) next to the modules of load().
+    ``utils.util_vis`` (matplotlib / imageio / trimesh plotting helpers, absent here) is replaced by an empty module: nothing
+    on the render / loss path touches it."""
+    global _pipelines
+    if _pipelines is not None:
+        return _pipelines
+    ref = load()
+    import importlib
+    import warnings
+    vis = types.ModuleType("utils.util_vis")
+    sys.modules["utils.util_vis"] = vis
+    sys.modules["utils"].util_vis = vis
+    sys.path.insert(0, REFERENCE_ROOT)
+    cwd = os.getcwd()
+    os.chdir(REFERENCE_ROOT)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cam = importlib.import_module("pipelines.Camera")
+            p3d = importlib.import_module("pipelines.Point3D")
+            ba = importlib.import_module("pipelines.BA")
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REFERENCE_ROOT)
+    _pipelines = types.SimpleNamespace(Camera=cam, Point3D=p3d, BA=ba, ref=ref)
+    return _pipelines
+
+
 @contextlib.contextmanager
 def in_reference_cwd():
     """The reference opens ``options/config_hash_sdf.json`` relative to its root (models/base.py:120)."""

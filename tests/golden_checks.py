@@ -279,3 +279,27 @@ def rays_case(device, seed=0):
     assert_close(c, c_ref, tol=1e-5, what="ray centers")
     assert_close(r, r_ref, tol=1e-5, what="ray directions")
     assert_close(p.grad, p_ref.grad, tol=1e-4, what="pose gradient")
+
+
+def se3_case(device, n=50, seed=0):
+    """ops.Se3ToSE3 (one kernel each way, forward-mode duals in the backward) vs the oracle restatement of utils/camera.py:85-96."""
+    from levels2fm_b200 import rays as rays_mod
+    g = torch.Generator().manual_seed(seed)
+    wu = torch.randn(n, 6, generator=g) * torch.tensor([0.7, 0.7, 0.7, 2.0, 2.0, 2.0])
+    wu[0] = 0.0
+    wu[1, :3] = 0.0                           # pure translation: theta = 0 must be regular
+    wu[2, :3] *= 1e-4
+    c = torch.randn(n, 3, 4, generator=g)
+    w_ref = wu.clone().requires_grad_(True)
+    a = port.se3_to_SE3(w_ref)
+    (a * c).sum().backward()
+    w = wu.clone().to(device).requires_grad_(True)
+    b = rays_mod.se3_to_SE3(w)
+    (b * c.to(device)).sum().backward()
+    assert_close(b, a, tol=1e-6, what="se3_to_SE3")
+    assert torch.isfinite(w.grad).all()
+    # torch's norm() has a zero subgradient at w = 0 where the true derivative of theta^2 terms is 0 as well; rows 2.. compare fully
+    assert_close(w.grad[2:], w_ref.grad[2:], tol=1e-5, what="se3_to_SE3 gradient")
+    assert_close(w.grad[:2, 3:], w_ref.grad[:2, 3:], tol=1e-5, what="se3_to_SE3 translation gradient at theta = 0")
+    # batched leading shape
+    assert rays_mod.se3_to_SE3(wu.view(5, n // 5, 6).to(device)).shape == (5, n // 5, 3, 4)

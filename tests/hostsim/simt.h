@@ -235,6 +235,8 @@ static inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }

@@ -353,3 +353,84 @@ def test_aabb_grad_flag_reproduces_reference_error():
 def test_radf_geometry_feat_position_gradient():
     from . import input_grad_checks as ig
     ig.radf_geometry_feat_input_grad(DEV, n=1000)
+
+
+# ----------------------------------------------------------------------------- forward-only entry points
+@pytest.mark.parametrize("use_bounds,dataset,N", [(False, "DTU", 32), (True, "ETH3D", 24), (True, "bmvs", 17)])
+def test_sdf_grid_volume_matches_reference_point_arithmetic(use_bounds, dataset, N):
+    from . import inference_checks as ic
+    vs = {"DTU": 2.0, "ETH3D": 10.0, "bmvs": 4.0}[dataset]
+    ic.grid_case(DEV, N=N, dataset=dataset, volume_size=vs, use_bounds=use_bounds, chunk=5000)
+
+
+@pytest.mark.parametrize("dual,eb", [(False, False), (True, False), (False, True)])
+def test_render_image_in_slices(dual, eb):
+    from . import inference_checks as ic
+    ic.image_case(DEV, H=48, W=64, dual=dual, slice_rays=1000, eb=eb)
+
+
+# ----------------------------------------------------------------------------- matched loss
+@pytest.mark.parametrize("eb", [False, True])
+def test_matched_loss_over_100_adam_steps(eb):
+    """North-star "at matched loss": identical initial state, 100 Adam steps (the reference's BA learning rates, lr_sdf 1e-4 /
+    lr_color 1e-3, options/LevelS2fM.yaml:75-82) of the render loss (10^3 L1 rgb + 10^2 eikonal) on the product, on the oracle in
+    fp32 and on the oracle in fp64, all on the same GPU.
+      * step 0: the loss agrees to <= 1e-4 relative -- measured 1e-6.
+      * the curve: BASELINE.md's "<= 1e-3 over 100 Adam steps" is NOT attainable by any fp32 implementation -- Adam's sign-like
+        updates amplify 1e-7 gradient rounding, and the oracle itself moves by 1e-2..1e-1 between fp32 and fp64
+        (profiles/matched_loss_probe_r2.txt).  The meaningful bar, asserted here: the product stays as close to the fp32 oracle
+        as the fp32 oracle stays to its own fp64 run (x3), and reaches the same loss level."""
+    from levels2fm_b200 import synthetic
+    over = {"SDF.VolSDF.volsdf_sampling": True, "SDF.VolSDF.sample_intvs": 32, "SDF.VolSDF.final_sample_intvs": 32} if eb else {}
+    opt = common.make_opt("DTU", DEV, 16, (None, 64, 64, 64, 16), 64, False, **over)
+    cfg = common.cfg_of(opt, 16)
+    sdf_sd, rad_sd = port.random_state(cfg, seed=1, table_std=1e-4, generic_weights=False)      # the benchmark's "init" scene
+    sdf, rad, ren = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    rad.load_state_dict(rad_sd)
+    n_rays, steps, lr_sdf, lr_col = 256, 100, 1e-4, 1e-3
+    center, ray = synthetic.make_rays(1, n_rays, 1.0, 1200, 1600, seed=3)
+    gt = torch.rand(1, n_rays, 3, generator=torch.Generator().manual_seed(4))
+    center, ray, gt = center.to(DEV), ray.to(DEV), gt.to(DEV)
+    curves = {}
+    o = torch.optim.Adam([{"params": sdf.parameters(), "lr": lr_sdf}, {"params": rad.parameters(), "lr": lr_col}])
+    c = []
+    for it in range(steps + 1):
+        o.zero_grad(set_to_none=True)
+        loss = synthetic.render_loss(ren.forward(opt, center, ray, sdf, rad), gt)
+        loss.backward()
+        c.append(float(loss.detach()))
+        o.step()
+    curves["ours"] = c
+    for name, dt in (("port32", torch.float32), ("port64", torch.float64)):
+        s1 = {k: v.detach().clone().to(DEV).to(dt).requires_grad_(True) for k, v in sdf_sd.items()}
+        r1 = {k: v.detach().clone().to(DEV).to(dt).requires_grad_(True) for k, v in rad_sd.items()}
+        o = torch.optim.Adam([{"params": list(s1.values()), "lr": lr_sdf}, {"params": list(r1.values()), "lr": lr_col}])
+        c = []
+        for it in range(steps + 1):
+            o.zero_grad(set_to_none=True)
+            loss = synthetic.render_loss(port.render_forward(center.to(dt), ray.to(dt), s1, r1, cfg), gt.to(dt))
+            loss.backward()
+            c.append(float(loss.detach()))
+            o.step()
+        curves[name] = c
+    t = {k: torch.tensor(v, dtype=torch.float64) for k, v in curves.items()}
+
+    def rel(a, b):
+        return (t[a] - t[b]).abs() / t[b].abs()
+    assert rel("ours", "port32")[0].item() < 1e-4, rel("ours", "port32")[0].item()
+    assert t["port32"][-1] < 0.5 * t["port32"][0] and t["ours"][-1] < 0.5 * t["ours"][0]        # the optimisation moves the loss
+    envelope = max(rel("port32", "port64").max().item(), 1e-3)
+    assert rel("ours", "port32").max().item() < 3 * envelope, (rel("ours", "port32").max().item(), envelope)
+    assert rel("ours", "port32").median().item() < 3 * max(rel("port32", "port64").median().item(), 1e-4)
+
+
+# ----------------------------------------------------------------------------- fused loss tail (SURVEY 8f row 1)
+@pytest.mark.parametrize("eik_masked,none_finished", [(True, False), (False, False), (True, True)])
+def test_fused_loss_tail_matches_reference_tail(eik_masked, none_finished):
+    from . import loss_checks as lc
+    lc.tail_case(DEV, B=2, R=4096, N=128, eik_masked=eik_masked, none_finished=none_finished)
+
+
+def test_se3_to_SE3_kernel_matches_oracle():
+    gc.se3_case(DEV, n=5000)

@@ -294,3 +294,51 @@ def test_aabb_grad_flag_reproduces_reference_error():
 def test_radf_geometry_feat_position_gradient():
     from . import input_grad_checks as ig
     ig.radf_geometry_feat_input_grad("cpu", n=60)
+
+
+# ----------------------------------------------------------------------------- forward-only entry points
+@pytest.mark.parametrize("use_bounds,dataset", [(False, "DTU"), (True, "ETH3D")])
+def test_sdf_grid_volume_matches_reference_point_arithmetic(use_bounds, dataset):
+    from . import inference_checks as ic
+    ic.grid_case("cpu", N=9, dataset=dataset, volume_size=2.0 if not use_bounds else 10.0, use_bounds=use_bounds, chunk=200)
+
+
+@pytest.mark.parametrize("dual", [False, True])
+def test_render_image_in_slices(dual):
+    from . import inference_checks as ic
+    ic.image_case("cpu", H=6, W=8, dual=dual, slice_rays=20)
+
+
+# ----------------------------------------------------------------------------- fused loss tail
+@pytest.mark.parametrize("eik_masked,none_finished", [(True, False), (False, False), (True, True)])
+def test_fused_loss_tail_matches_reference_tail(eik_masked, none_finished):
+    from . import loss_checks as lc
+    lc.tail_case("cpu", eik_masked=eik_masked, none_finished=none_finished)
+
+
+def test_gradient_bucket_direct_scatter_equals_autograd_accumulation():
+    """parallel.GradBucket(direct=True): the backward kernels scatter the table gradient straight into the bucket (no zero-filled
+    temporary + autograd add); same numbers as the plain autograd route, and a second backward accumulates."""
+    from levels2fm_b200 import parallel, synthetic
+    opt = common.make_opt("DTU", "cpu", 16, (None, 64, 16), 8, True)
+    res = {}
+    for direct in (True, False):
+        torch.manual_seed(0)
+        sdf, rad, ren = common.build_models(opt)
+        cfg = common.cfg_of(opt, 16)
+        sdf_sd, rad_sd = port.random_state(cfg, seed=3, table_std=0.2)
+        sdf.load_state_dict(sdf_sd)
+        rad.load_state_dict(rad_sd)
+        bucket = parallel.GradBucket(list(sdf.parameters()) + list(rad.parameters()), direct=direct)
+        center, ray = common.make_rays(1, 6, 1.0)
+        gt = torch.rand(1, 6, 3, generator=torch.Generator().manual_seed(1))
+        for _ in range(2):
+            synthetic.render_loss_fused(ren.forward(opt, center, ray, sdf, rad), gt).backward()
+        assert all(p.grad.data_ptr() == bucket.flat[o:o + 1].data_ptr() for p, o in zip(bucket.params, bucket.offsets))
+        res[direct] = bucket.flat.clone()
+    assert float(res[False].abs().max()) > 0
+    assert common.rel_err(res[True], res[False]) < 1e-6
+
+
+def test_se3_to_SE3_kernel_matches_oracle():
+    gc.se3_case("cpu")

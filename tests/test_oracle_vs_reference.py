@@ -58,3 +58,19 @@ def test_render_forward_backward_matches_reference(ref):
     for mod, sd in ((sdf, sdf_sd), (rad, rad_sd)):
         for k, p in mod.named_parameters():
             assert torch.allclose(p.grad, sd[k].grad, rtol=1e-4, atol=1e-6), k
+
+
+def test_se3_to_SE3_matches_reference():
+    """oracle/port.se3_to_SE3 vs the reference's own Lie.se3_to_SE3 (utils/camera.py:85-96), values and gradients."""
+    ref = ref_shim.load()
+    g = torch.Generator().manual_seed(0)
+    wu = torch.randn(9, 6, generator=g) * torch.tensor([0.7, 0.7, 0.7, 2.0, 2.0, 2.0])
+    wu[0, :3] = 0.0                          # the identity rotation (theta = 0)
+    wu[1, :3] *= 1e-4
+    w_ref, w_port = wu.clone().requires_grad_(True), wu.clone().requires_grad_(True)
+    a, b = ref.camera.lie.se3_to_SE3(w_ref), port.se3_to_SE3(w_port)
+    assert torch.allclose(a, b, atol=1e-6, rtol=1e-6)
+    c = torch.randn(a.shape, generator=g)
+    (a * c).sum().backward()
+    (b * c).sum().backward()
+    assert torch.allclose(w_ref.grad[1:], w_port.grad[1:], atol=1e-5, rtol=1e-5)

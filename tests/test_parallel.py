@@ -44,8 +44,8 @@ def _worker(rank, world, port_no, q):
     bucket.zero()
     loss = loss_sum(c_loc, r_loc, gt_loc)
     loss.backward()
-    assert all(p.grad.data_ptr() == bucket.flat[o:o + 1].data_ptr() for p, o in
-               zip(bucket.params, torch.tensor([0] + [p.numel() for p in bucket.params[:-1]]).cumsum(0).tolist()))
+    assert all(p.grad.data_ptr() == bucket.flat[o:o + 1].data_ptr() for p, o in zip(bucket.params, bucket.offsets))
+    assert all(o % 4 == 0 for o in bucket.offsets)          # 16-byte aligned views: the fused backward scatters with vector atomics
     bucket.extra[0] = loss.detach()
     bucket.allreduce()
     reduced = bucket.flat.clone()
@@ -55,8 +55,10 @@ def _worker(rank, world, port_no, q):
     full = loss_sum(center, ray, gt)
     full.backward()
     ref = torch.cat([p.grad.reshape(-1) for p in params])
-    err = (reduced[:ref.numel()] - ref).abs().max().item() / ref.abs().max().item()
-    q.put((rank, err, abs(reduced[ref.numel()].item() - full.item()) / abs(full.item())))
+    got = torch.cat([reduced[o:o + p.numel()] for p, o in zip(bucket.params, bucket.offsets)])
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    n_flat = bucket.flat.numel() - bucket.extra.numel()
+    q.put((rank, err, abs(reduced[n_flat].item() - full.item()) / abs(full.item())))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -93,6 +95,7 @@ def test_bucket_views_survive_zero_and_accumulate():
     ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
     b = parallel.GradBucket(ps, extra=2)
     (ps[0].sum() * 2 + ps[1].sum() * 3).backward()
+    assert b.offsets == [0, 12]
     assert torch.equal(b.flat[:12], torch.full((12,), 2.0)) and torch.equal(b.flat[12:17], torch.full((5,), 3.0))
     (ps[0].sum()).backward()                       # accumulates in place into the same storage
     assert torch.equal(b.flat[:12], torch.full((12,), 3.0))
