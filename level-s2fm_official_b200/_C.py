@@ -14,7 +14,8 @@ from typing import Optional, Sequence
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libls2fm_sm100.so")
+# LS2FM_LIB: an alternative build of the SAME sources (e.g. the -DLS_ABLATE timing experiment of tools/ablate.sh); never a CPU path
+LIB_PATH = os.environ.get("LS2FM_LIB") or os.path.join(HERE, "lib", "libls2fm_sm100.so")
 
 MAX_LEVELS = 16
 MAX_LAYERS = 4

@@ -127,6 +127,9 @@ static void ls_fill_args(LsFieldArgs& a, const ls2fm_field_t* field, const ls2fm
     if (rad) a.r = *rad;
     for (int d = 0; d < 3; ++d) a.inv_ext[d] = 1.0f / (field->bound_max[d] - field->bound_min[d]);
     a.s = field->sdf_sign / field->scale_mlp;
+#if defined(LS_ABLATE)
+    { const char* e = getenv("LS2FM_ABLATE"); a.dbg = e ? atoi(e) : 0; }
+#endif
 }
 
 extern "C" {

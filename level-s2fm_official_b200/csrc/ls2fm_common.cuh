@@ -157,6 +157,29 @@ LS_DEV void ls_corner_indices(uint32_t resolution, uint32_t size, uint32_t hashe
     }
 }
 
+// Table-gradient scatter of an x-neighbour corner pair (entries i0, i1 of one level; 2 floats each).  When the two entries form an
+// aligned 16-byte pair -- always for an even cell of a hashed level (i1 == i0 ^ 1), for every other cell of a dense one -- ONE
+// 16-byte vector atomic (red.global.add.v4.f32, sm_90+) replaces two 8-byte ones: the L1TEX / L2 atomic path costs the same per
+// lane for either width (tools/probe/gather_probe.cu: 0.66 lane-atomics per SM per cycle for RED.64 and RED.128 alike), so the
+// scatter's lane count -- what bounds it -- drops by a quarter.  tab must be 16-byte aligned for v4 (pass v4 = false otherwise).
+LS_DEV void ls_red_pair(float* tab, uint32_t i0, uint32_t i1, float a0, float a1, float b0, float b1, bool v4) {
+#if defined(LS_HOSTSIM)
+    (void)v4;
+    tab[2 * (size_t)i0] += a0; tab[2 * (size_t)i0 + 1] += a1;
+    tab[2 * (size_t)i1] += b0; tab[2 * (size_t)i1 + 1] += b1;
+#else
+    if (v4 && ((i0 ^ i1) == 1u)) {
+        const bool swap = (i0 & 1u) != 0u;
+        float* p = tab + 2 * (size_t)(i0 & ~1u);
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(swap ? b0 : a0), "f"(swap ? b1 : a1),
+                     "f"(swap ? a0 : b0), "f"(swap ? a1 : b1) : "memory");
+    } else {
+        atomicAdd(reinterpret_cast<float2*>(tab) + i0, make_float2(a0, a1));
+        atomicAdd(reinterpret_cast<float2*>(tab) + i1, make_float2(b0, b1));
+    }
+#endif
+}
+
 // world -> unit cube exactly as models/base.py:35: (x - bmin) / (bmax - bmin)
 LS_DEV void ls_world_to_unit(const float bmin[3], const float bmax[3], const float x[3], float u[3]) {
 #pragma unroll

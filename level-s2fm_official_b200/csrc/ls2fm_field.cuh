@@ -57,7 +57,13 @@ struct LsFieldArgs {
     const float* saved_nrm; const float* saved_rgb;
     float* d_table; float* d_theta; float* d_w_eff; float* d_b_eff; float* d_geo2;
     ls2fm_input_grads_t ig;   // gradients w.r.t. the sample positions (all NULL: not wanted)
+    int dbg;                  // LS_ABLATE builds only (tools/ablate.py): bit 0 no scatter, 1 no gather loads, 2 no weight-gradient MMAs
 };
+#if defined(LS_ABLATE)
+#define LS_DBG(a, bit) (((a).dbg >> (bit)) & 1)
+#else
+#define LS_DBG(a, bit) 0
+#endif
 
 inline int ls_round4(int v) { return (v + 3) & ~3; }
 
@@ -222,7 +228,7 @@ LS_DEV int64_t ls_n_samples(const ls2fm_points_t& p) {
 }
 
 // one level of the hash grid at u: features h[2] and dh/du [2][3]
-LS_DEV void ls_level_eval(const ls2fm_field_t& f, int l, const float u[3], float h[2], float dh[2][3]) {
+LS_DEV void ls_level_eval(const ls2fm_field_t& f, int l, const float u[3], float h[2], float dh[2][3], int nogather = 0) {
     const float scale = f.levels[l].scale;
     const uint32_t res = f.levels[l].resolution, size = f.levels[l].size, hashed = f.levels[l].hashed;
     const float* tab = f.table + 2 * (size_t)f.levels[l].offset;
@@ -232,7 +238,7 @@ LS_DEV void ls_level_eval(const ls2fm_field_t& f, int l, const float u[3], float
     uint32_t ci[8];
     ls_corner_indices<0, 8>(res, size, hashed, c, ci);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float2*>(tab) + ci[k]);
+    for (int k = 0; k < 8; ++k) v[k] = nogather ? make_float2(0.01f * (float)(ci[k] & 7), 0.02f) : __ldg(reinterpret_cast<const float2*>(tab) + ci[k]);
     const float w0 = c.w[0], w1 = c.w[1], w2 = c.w[2];
     const float m0 = 1.f - w0, m1 = 1.f - w1, m2 = 1.f - w2;
 #pragma unroll

@@ -99,7 +99,8 @@ LS_DEV void ls_bt_matrix(const LsTcNet& img, int H, int b, int* src, int* floats
 // (Rounding one operand to tf32 instead of carrying its lo part was tried: the 2^-12 noise per term does not average out against
 //  the gradient -- a sum of large cancelling terms -- and showed up as 3e-3 of the output layer's weight_g gradient on 16 k samples.)
 LS_DEV void ls_bt_wgrad(uint32_t tmem, int d_col, const float* a_raw, const float* a_lo, int a_lbo, const float* b_raw, const float* b_lo,
-                        int b_lbo, int N) {
+                        int b_lbo, int N, int skip = 0) {
+    if (skip) return;
 #if defined(LS_HOSTSIM)
     for (int ks = 0; ks < LS_BT_KG / 2; ++ks) {      // 8 rows (two groups of 4) per MMA
         const int ao = ks * 2 * (a_lbo / 4), bo = ks * 2 * (b_lbo / 4);
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         if (plane) ls_corner_indices<4, 4>(res, size, hashed, c, ci);
         else ls_corner_indices<0, 4>(res, size, hashed, c, ci);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = __ldg(tab + ci[k]);
+        for (int k = 0; k < 4; ++k) v[k] = LS_DBG(a, 1) ? make_float2(0.01f * (float)(ci[k] & 7), 0.02f) : __ldg(tab + ci[k]);
         const float w0 = c.w[0], w1 = c.w[1], w2 = c.w[2];
         const float m0 = 1.f - w0, m1 = 1.f - w1, m2 = 1.f - w2;
         float nbar[3];
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
     bool sc_pending = false;
     auto scatter_level = [&](int buf, int r, float e0, float e1, float t0, float t1) {
         const float* P = PBN + (buf * LS_BT_TILE + sl) * LS_BT_PBP;
-        if (!a.d_table || P[15] == 0.f) return;
+        if (!a.d_table || P[15] == 0.f || LS_DBG(a, 0)) return;
         const float u[3] = {P[16], P[17], P[18]};
         float nbar[3];
         load_nbar(P, nbar);
@@ -358,15 +359,16 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         for (int d = 0; d < 3; ++d) ns[d] = nbar[d] * scale * a.inv_ext[d];
         uint32_t ci[8];
         ls_corner_indices<0, 8>(res, size, hashed, c, ci);
+        const bool v4 = (reinterpret_cast<uintptr_t>(a.d_table) & 15) == 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float f0 = (k & 1) ? c.w[0] : 1.f - c.w[0];
+        for (int k = 0; k < 8; k += 2) {        // x-neighbour pairs: one 16-byte atomic when the two entries are an aligned pair
             const float f1 = (k & 2) ? c.w[1] : 1.f - c.w[1];
             const float f2 = (k & 4) ? c.w[2] : 1.f - c.w[2];
-            const float wgt = f0 * f1 * f2;
-            const float dw = ((k & 1) ? ns[0] : -ns[0]) * f1 * f2 + ((k & 2) ? ns[1] : -ns[1]) * f0 * f2 +
-                             ((k & 4) ? ns[2] : -ns[2]) * f0 * f1;
-            atomicAdd(reinterpret_cast<float2*>(tab) + ci[k], make_float2(wgt * e0 + dw * t0, wgt * e1 + dw * t1));
+            const float m0 = 1.f - c.w[0], w0 = c.w[0];
+            const float dyz = ((k & 2) ? ns[1] : -ns[1]) * f2 + ((k & 4) ? ns[2] : -ns[2]) * f1;       // d(f1 f2) along nbar
+            const float wa = m0 * f1 * f2, wb = w0 * f1 * f2;
+            const float da = -ns[0] * f1 * f2 + m0 * dyz, db = ns[0] * f1 * f2 + w0 * dyz;
+            ls_red_pair(tab, ci[k], ci[k + 1], wa * e0 + da * t0, wa * e1 + da * t1, wb * e0 + db * t0, wb * e1 + db * t1, v4);
         }
     };
     const bool has_levels = 4 * cg < L;
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                     ls_tc_commit(bar);
                     // ... then the output-layer weight gradient, transposed: D[i][o] += sum_r a_H[r][i] ybar'[r][o] (columns
                     // dout..dout+2: G[c][i]); it runs under the next epilogue and is only waited for before the staging arrays change
-                    ls_bt_wgrad(tmem, LS_BT_WG, AR, AL, LS_BT_LBO, ZR, ZL, LS_BT_LBO, 32);
+                    ls_bt_wgrad(tmem, LS_BT_WG, AR, AL, LS_BT_LBO, ZR, ZL, LS_BT_LBO, 32, LS_DBG(a, 2));
                     ls_tc_commit(bar2);
                 }
             }
@@ -662,11 +664,11 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
                     if (k > 1) {
                         issue_x3(LS_BT_D, colA, LS_BT_LO, LS_H, LS_H);
                         ls_tc_commit(bar);
-                        ls_bt_wgrad(tmem, LS_BT_WG + 64 * (k - 1), ZR, ZL, LS_BT_LBO, AR, AL, LS_BT_LBO, LS_H);
+                        ls_bt_wgrad(tmem, LS_BT_WG + 64 * (k - 1), ZR, ZL, LS_BT_LBO, AR, AL, LS_BT_LBO, LS_H, LS_DBG(a, 2));
                     } else {
                         issue_x3(LS_BT_D, colA, LS_BT_LO, img.n_in_pad[0], LS_H);
                         ls_tc_commit(bar);
-                        ls_bt_wgrad(tmem, LS_BT_WG + 24, ZR, ZL, LS_BT_LBO, ES, AL, LS_BT_LBO_E, LS_BT_EROWS);
+                        ls_bt_wgrad(tmem, LS_BT_WG + 24, ZR, ZL, LS_BT_LBO, ES, AL, LS_BT_LBO_E, LS_BT_EROWS, LS_DBG(a, 2));
                     }
                     ls_tc_commit(bar2);
                 }

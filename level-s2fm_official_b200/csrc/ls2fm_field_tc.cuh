@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_forward_tc_kernel(c
             for (int r = 0; r < 4; ++r) {
                 const int l = 4 * cg + r;
                 float h[2], dh[2][3];
-                ls_level_eval(a.f, l, u, h, dh);        // L % 4 == 0 on this path: all four levels of the group exist
+                ls_level_eval(a.f, l, u, h, dh, LS_DBG(a, 1));        // L % 4 == 0 on this path: all four levels of the group exist
                 e8[2 * r] = h[0]; e8[2 * r + 1] = h[1];
 #pragma unroll
                 for (int fi = 0; fi < 2; ++fi)
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(LS_TC_THREADS, 1) ls_field_sdf_tc_kernel(const
             for (int r = 0; r < 4; ++r) {
                 const int l = 4 * cg + r;
                 float h[2], dh[2][3];
-                ls_level_eval(a.f, l, u, h, dh);        // L % 4 == 0 on this path: all four levels of the group exist
+                ls_level_eval(a.f, l, u, h, dh, LS_DBG(a, 1));        // L % 4 == 0 on this path: all four levels of the group exist
                 e8[2 * r] = h[0]; e8[2 * r + 1] = h[1];
             }
 #pragma unroll
