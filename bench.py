@@ -387,6 +387,9 @@ def main():
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--symmetric", action="store_true", help="N > 1: gradient bucket in symmetric memory, NVLS multimem all-reduce")
     ap.add_argument("--e2e-sync-readback", action="store_true", help="diagnostic: read the loss back with .item() every step")
+    ap.add_argument("--graph", choices=["on", "off"], default="on",
+                    help="replay the iteration's compute (sampler .. backward) as one CUDA graph (levels2fm_b200.graph.GraphedStep); "
+                         "workloads with a host read-back (c4: sphere_tracing) always run eagerly")
     args = ap.parse_args()
     if args.workload in FORWARD_ONLY:
         if args.impl == "reference":
@@ -446,7 +449,7 @@ def main():
     # per-rank gradients is the gradient of the global mean; rays_rank / rays_step = 1 / world
     loss_scale = rays_rank / rays_step if world > 1 else 1.0
 
-    def step(c, r, g):
+    def compute(c, r, g):
         bucket.zero()
         out = ren.forward(opt, c, r, sdf, rad)
         loss = synthetic.render_loss_fused(out, g)
@@ -456,8 +459,25 @@ def main():
         if loss_scale != 1.0:
             loss = loss * loss_scale
         loss.backward()
+        return loss.detach(), out["sdfs_volume"].detach()
+
+    use_graph = args.graph == "on" and not wl.get("trace")
+    graphed = None
+    launches_per_step = None
+    if use_graph:
+        from levels2fm_b200.graph import GraphedStep
+        try:
+            ops.KLOG.reset()
+            graphed = GraphedStep(compute, (center, ray, gt), warmup=W)
+            launches_per_step = ops.KLOG.total() // (W + 1)          # W eager warm-up runs + the captured one
+        except Exception as e:          # capture is an optimisation, never a requirement
+            sys.stderr.write(f"CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly\n")
+            graphed, use_graph = None, False
+
+    def step(c, r, g):
+        loss, sv = graphed(c, r, g) if graphed is not None else compute(c, r, g)
         bucket.allreduce()
-        return loss, out
+        return loss, {"sdfs_volume": sv}
 
     def sync_all():
         torch.cuda.synchronize()
@@ -484,7 +504,7 @@ def main():
         b.record()
         evs.append((a, b))
     sync_all()
-    launches = ops.KLOG.total()
+    launches = ops.KLOG.total() if launches_per_step is None else launches_per_step * args.steps
     clk = clocks.stop()
     step_ms = [a.elapsed_time(b) for a, b in evs]
     t_local = sum(step_ms)
@@ -535,7 +555,7 @@ def main():
     for _ in range(n_prof):
         flush.fill_(1.0)
         torch.cuda._sleep(int(8e6))      # ~4 ms of device-side spin: the host runs ahead, so every event pair brackets exactly its kernel
-        step(center, ray, gt)
+        compute(center, ray, gt)         # (eager: the events sit between the launches)
     torch.cuda.synchronize()
     ops.KLOG.timing = False
     launch_list = ops.KLOG.launches()
@@ -582,6 +602,7 @@ def main():
                 "config": {"workload": wl["desc"], "name": args.workload, "rays_per_gpu": rays_rank, "rays_per_step": rays_step,
                            "samples_per_ray": int(n_samples), "regime": args.regime,
                            "l2": "flushed between timed steps (256 MB fill, untimed), in the device-resident loop AND in the e2e loop",
+                           "cuda_graph": bool(use_graph),
                            "parallelism": f"ray-parallel dp{world}, one flat-bucket all-reduce per step" + (f" ({bucket.collective})" if world > 1 else "")},
                 "clocks": clk, "gpu_launches": launches,
                 "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

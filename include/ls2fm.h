@@ -145,9 +145,10 @@ typedef struct {
  * models/base.py:230,257).  One launch instead of ~30 eager kernels. */
 int ls2fm_params_forward(const ls2fm_param_layer_t* geo, int32_t n_geo, const ls2fm_param_layer_t* rad,
                          float* theta, float* w_eff, float* b_eff, void* stream);
-/* backward: d_theta / d_w_eff / d_b_eff (nullable) -> dg, dv, db of every layer (written). */
+/* backward: d_theta / d_w_eff / d_b_eff (nullable) -> dg, dv, db of every layer: written, or added to when accumulate != 0
+ * (the caller points dg / dv / db straight at the parameters' .grad buffers: no temporaries, no autograd accumulation kernels). */
 int ls2fm_params_backward(const ls2fm_param_layer_t* geo, int32_t n_geo, const ls2fm_param_layer_t* rad,
-                          const float* d_theta, const float* d_w_eff, const float* d_b_eff, void* stream);
+                          const float* d_theta, const float* d_w_eff, const float* d_b_eff, int32_t accumulate, void* stream);
 
 /* ------------------------------------------------------------------ tensor-core operand image
  * The tcgen05 forward kernel wants the weights as hi/lo TF32 operands in its shared-memory layout (W_l and W_l^T, K-major

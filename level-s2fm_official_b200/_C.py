@@ -83,7 +83,7 @@ SIGNATURES = {
     "ls2fm_grid_encode": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP]),
     "ls2fm_grid_encode_backward": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP, _VP]),
     "ls2fm_params_forward": (C.c_int, [C.POINTER(ParamLayer), C.c_int32, C.POINTER(ParamLayer), _VP, _VP, _VP, _VP]),
-    "ls2fm_params_backward": (C.c_int, [C.POINTER(ParamLayer), C.c_int32, C.POINTER(ParamLayer), _VP, _VP, _VP, _VP]),
+    "ls2fm_params_backward": (C.c_int, [C.POINTER(ParamLayer), C.c_int32, C.POINTER(ParamLayer), _VP, _VP, _VP, C.c_int32, _VP]),
     "ls2fm_field_image_floats": (C.c_int64, [C.POINTER(Field), C.POINTER(Radiance)]),
     "ls2fm_field_prepare": (C.c_int, [C.POINTER(Field), C.POINTER(Radiance), _VP, _VP]),
     "ls2fm_field_forward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),

@@ -254,10 +254,10 @@ int ls2fm_params_forward(const ls2fm_param_layer_t* geo, int32_t n_geo, const ls
 }
 
 int ls2fm_params_backward(const ls2fm_param_layer_t* geo, int32_t n_geo, const ls2fm_param_layer_t* rad, const float* d_theta,
-                          const float* d_w_eff, const float* d_b_eff, void* stream) {
+                          const float* d_w_eff, const float* d_b_eff, int32_t accumulate, void* stream) {
     LsParamArgs a;
     if (ls_fill_params(a, geo, n_geo, rad, true)) return 1;
-    a.d_theta = d_theta; a.d_w_eff = d_w_eff; a.d_b_eff = d_b_eff;
+    a.d_theta = d_theta; a.d_w_eff = d_w_eff; a.d_b_eff = d_b_eff; a.accumulate = accumulate ? 1 : 0;
     const int smem = LS_PP_SMEM_FLOATS * (int)sizeof(float);
     if (ls_opt_in_smem(ls_params_backward_kernel, smem)) return 1;
     LS_LAUNCH(ls_params_backward_kernel, (unsigned)(1 + n_geo), LS_PP_THREADS, smem, stream, a);

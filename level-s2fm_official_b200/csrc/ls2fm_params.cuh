@@ -23,7 +23,9 @@ struct LsParamArgs {
     int has_rad;                    // radiance decoder with exactly 3 weight-normed layers: in -> 64 -> 64 -> 3
     float* theta; float* w_eff; float* b_eff;                        // forward outputs
     const float* d_theta; const float* d_w_eff; const float* d_b_eff;   // backward inputs (nullable)
+    int accumulate;                 // backward: dg / dv / db += instead of = (every element has exactly one writer thread)
 };
+LS_DEV void ls_pp_out(float* p, float v, int acc) { *p = acc ? *p + v : v; }
 
 // effective (weight-normed) matrix of one layer into shared memory, row-major [dout][pitch]; one warp per row
 LS_DEV void ls_pp_effective(const LsParamLayer& L, float* W, int pitch, int tid, int nt) {
@@ -38,7 +40,7 @@ LS_DEV void ls_pp_effective(const LsParamLayer& L, float* W, int pitch, int tid,
 }
 
 // weight-norm backward of one layer: dW (row-major [dout][pitch], shared memory) -> dg, dv; one warp per row
-LS_DEV void ls_pp_weightnorm_bwd(const LsParamLayer& L, const float* dW, int pitch, int tid, int nt) {
+LS_DEV void ls_pp_weightnorm_bwd(const LsParamLayer& L, const float* dW, int pitch, int tid, int nt, int acc) {
     const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     for (int j = warp; j < L.dout; j += nw) {
         float n2 = 0.f, dot = 0.f;
@@ -50,9 +52,9 @@ LS_DEV void ls_pp_weightnorm_bwd(const LsParamLayer& L, const float* dW, int pit
         n2 = ls_warp_sum(n2);
         dot = ls_warp_sum(dot);
         const float inv = 1.f / sqrtf(n2);
-        if (lane == 0) L.dg[j] = dot * inv;                    // dW . v / ||v||
+        if (lane == 0) ls_pp_out(L.dg + j, dot * inv, acc);    // dW . v / ||v||
         const float c = L.g[j] * inv, k = dot * inv * inv;     // dv = g/||v|| (dW - (dW . v) v / ||v||^2)
-        for (int i = lane; i < L.din; i += 32) L.dv[j * L.din + i] = c * (dW[j * pitch + i] - k * L.v[j * L.din + i]);
+        for (int i = lane; i < L.din; i += 32) ls_pp_out(L.dv + j * L.din + i, c * (dW[j * pitch + i] - k * L.v[j * L.din + i]), acc);
     }
 }
 
@@ -137,8 +139,9 @@ __global__ void __launch_bounds__(LS_PP_THREADS, 1) ls_params_backward_kernel(co
             dot = ls_warp_sum(dot);
             const float inv = 1.f / sqrtf(n2);
             const float c = L.g[j] * inv, k = dot * inv * inv;
-            for (int i = lane; i < L.din; i += 32) L.dv[j * L.din + i] = c * (a.d_theta[off + i * L.dout + j] - k * L.v[j * L.din + i]);
-            if (lane == 0) { L.dg[j] = dot * inv; L.db[j] = a.d_theta[off + L.din * L.dout + j]; }
+            for (int i = lane; i < L.din; i += 32)
+                ls_pp_out(L.dv + j * L.din + i, c * (a.d_theta[off + i * L.dout + j] - k * L.v[j * L.din + i]), a.accumulate);
+            if (lane == 0) { ls_pp_out(L.dg + j, dot * inv, a.accumulate); ls_pp_out(L.db + j, a.d_theta[off + L.din * L.dout + j], a.accumulate); }
         }
         return;
     }
@@ -201,9 +204,9 @@ __global__ void __launch_bounds__(LS_PP_THREADS, 1) ls_params_backward_kernel(co
         M[k * LS_PP_P1 + i] = acc;
     }
     __syncthreads();
-    ls_pp_weightnorm_bwd(a.rad[0], M, LS_PP_P1, tid, nt);
-    ls_pp_weightnorm_bwd(a.rad[1], dW2, LS_PP_P2, tid, nt);
-    ls_pp_weightnorm_bwd(a.rad[2], dW3, LS_PP_P2, tid, nt);
-    for (int j = tid; j < LS_H; j += nt) { a.rad[0].db[j] = db1[j]; a.rad[1].db[j] = dt[j]; }
-    if (tid < 3) a.rad[2].db[tid] = dwe[tid];
+    ls_pp_weightnorm_bwd(a.rad[0], M, LS_PP_P1, tid, nt, a.accumulate);
+    ls_pp_weightnorm_bwd(a.rad[1], dW2, LS_PP_P2, tid, nt, a.accumulate);
+    ls_pp_weightnorm_bwd(a.rad[2], dW3, LS_PP_P2, tid, nt, a.accumulate);
+    for (int j = tid; j < LS_H; j += nt) { ls_pp_out(a.rad[0].db + j, db1[j], a.accumulate); ls_pp_out(a.rad[1].db + j, dt[j], a.accumulate); }
+    if (tid < 3) ls_pp_out(a.rad[2].db + tid, dwe[tid], a.accumulate);
 }

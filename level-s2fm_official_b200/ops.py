@@ -298,13 +298,14 @@ def composite_forward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, b
 
 
 def composite_backward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bgcolor, g_rgb, g_depth, g_normal,
-                           want_d_ray=False, want_d_t=False):
+                           want_d_ray=False, want_d_t=False, d_beta=None):
     r, n = t.shape
     dev = t.device
     d_sdf = torch.empty(r, n, device=dev)
     d_rgbs = torch.empty(r, n, 3, device=dev) if rgbs is not None else None
     d_nrm = torch.empty(r, n, 3, device=dev) if nrm is not None else None
-    d_beta = torch.zeros(1, device=dev)
+    if d_beta is None:          # (else: the caller's accumulator, e.g. the gradient bucket's slot of SDF.beta -- the kernel adds)
+        d_beta = torch.zeros(1, device=dev)
     d_ray = torch.zeros(r, 3, device=dev) if want_d_ray else None
     d_t = torch.empty(r, n, device=dev) if want_d_t else None
     _call(lib, "composite_backward", lib.dll.ls2fm_composite_backward, lib.ptr(ray), lib.ptr(t), lib.ptr(sdf), lib.ptr(rgbs), lib.ptr(nrm), lib.ptr(beta_param), float(beta_speed),
@@ -394,9 +395,13 @@ class FieldEval(torch.autograd.Function):
         need = ctx.needs_input_grad
         sink = ctx.table_sink if need[2] else None
         d_table = sink if sink is not None else (torch.zeros_like(table) if need[2] else None)
-        d_theta = torch.zeros_like(theta) if need[3] else None
-        d_w = torch.zeros_like(w_eff) if with_rad else None
-        d_b = torch.zeros_like(b_eff) if with_rad else None
+        # one zero-fill for the three small accumulators (the kernels add into them with atomics)
+        n_t = theta.numel() if need[3] else 0
+        n_w, n_b = (w_eff.numel(), b_eff.numel()) if with_rad else (0, 0)
+        small = torch.zeros(n_t + n_w + n_b, device=table.device)
+        d_theta = small[:n_t] if need[3] else None
+        d_w = small[n_t:n_t + n_w].view_as(w_eff) if with_rad else None
+        d_b = small[n_t + n_w:] if with_rad else None
         d_geo2 = torch.empty_like(geo2) if (with_rad and geo2 is not None) else None
         d_xyz = d_center = d_ray = d_t = None
         if xyz is not None:
@@ -437,6 +442,7 @@ class Composite(torch.autograd.Function):
         ray, t, sdf = _c(ray.detach()), _c(t.detach()), _c(sdf.detach())
         rgbs = _c(rgbs.detach()) if rgbs is not None else None
         nrm = _c(nrm.detach()) if nrm is not None else None
+        ctx.beta_sink = grad_sink(beta_param)
         beta_param = beta_param.detach().contiguous()
         rgb, depth, normal, opacity = composite_forward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bgcolor)
         ctx.save_for_backward(ray, t, sdf, rgbs, nrm, beta_param)
@@ -456,10 +462,11 @@ class Composite(torch.autograd.Function):
         ray, t, sdf, rgbs, nrm, beta_param = ctx.saved_tensors
         beta_speed, bg = ctx.misc
         want_ray, want_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        sink = ctx.beta_sink if ctx.needs_input_grad[5] else None
         d_sdf, d_rgbs, d_nrm, d_beta, d_ray, d_t = composite_backward_raw(
             lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, bg, _c(g_rgb) if rgbs is not None else None, _c(g_depth),
-            _c(g_normal) if nrm is not None else None, want_ray, want_t)
-        return d_ray, d_t, d_sdf, d_rgbs, d_nrm, d_beta.view_as(beta_param), None, None
+            _c(g_normal) if nrm is not None else None, want_ray, want_t, d_beta=sink)
+        return d_ray, d_t, d_sdf, d_rgbs, d_nrm, None if sink is not None else d_beta.view_as(beta_param), None, None
 
 
 def _aabb_vjp(c, r, hits, g_near, g_far, bmin, bmax):
@@ -699,6 +706,8 @@ class ParamPrep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, n_geo, *tensors):
         lib = _C.get()
+        sinks = [grad_sink(t) for t in tensors]
+        ctx.sinks = sinks if all(s is not None for s in sinks) else None
         ts = [t.detach().contiguous() for t in tensors]
         geo = [tuple(ts[3 * i:3 * i + 3]) for i in range(n_geo)]
         rad = [tuple(ts[3 * (n_geo + i):3 * (n_geo + i) + 3]) for i in range((len(ts) - 3 * n_geo) // 3)]
@@ -719,12 +728,14 @@ class ParamPrep(torch.autograd.Function):
         lib = _C.get()
         ts = list(ctx.saved_tensors)
         n_geo, n_rad = ctx.n_geo, ctx.n_rad
-        grads = [torch.empty_like(t) for t in ts]
+        use_rad = n_rad == 3 and d_w_eff is not None and d_w_eff.numel() > 0
+        # with gradient sinks on every parameter (parallel.GradBucket(direct=True)) the kernel adds straight into the .grad buffers
+        direct = ctx.sinks is not None and all(ctx.needs_input_grad[1:]) and (n_rad == 0 or use_rad)
+        grads = list(ctx.sinks) if direct else [torch.empty_like(t) for t in ts]
         geo = [tuple(ts[3 * i:3 * i + 3]) for i in range(n_geo)]
         rad = [tuple(ts[3 * (n_geo + i):3 * (n_geo + i) + 3]) for i in range(n_rad)]
         ggeo = [tuple(grads[3 * i:3 * i + 3]) for i in range(n_geo)]
         grad_ = [tuple(grads[3 * (n_geo + i):3 * (n_geo + i) + 3]) for i in range(n_rad)]
-        use_rad = n_rad == 3 and d_w_eff is not None and d_w_eff.numel() > 0
         if n_rad == 3 and not use_rad:
             for g in grads[3 * n_geo:]:
                 g.zero_()
@@ -735,7 +746,9 @@ class ParamPrep(torch.autograd.Function):
         _call(lib, "params_backward", lib.dll.ls2fm_params_backward, _param_layers(lib, geo, ggeo) if geo else None, n_geo,
               _param_layers(lib, rad, grad_) if use_rad else None,
               lib.ptr(d_theta.contiguous()) if n_geo else None, lib.ptr(d_w_eff.contiguous()) if use_rad else None,
-              lib.ptr(d_b_eff.contiguous()) if use_rad else None, lib.stream())
+              lib.ptr(d_b_eff.contiguous()) if use_rad else None, 1 if direct else 0, lib.stream())
+        if direct:
+            return (None,) * (1 + len(ts))
         return (None, *grads)
 
 

@@ -23,7 +23,7 @@ def lib():
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "ls2fm.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ls2fm_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(ls2fm_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_every_declared_symbol_is_exported_and_bound(lib):
