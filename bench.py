@@ -70,6 +70,9 @@ FORWARD_ONLY = {
              "(pipelines/Camera.py:275-311), shipped DTU networks, 128 uniform samples/ray",
     "grid": "forward only (SURVEY 8f row 4): the 512^3 SDF volume of utils/util.py:392-430 (extract_mesh), shipped DTU SDF network, "
             "points generated on the device, values-only tensor-core kernel",
+    "ba_sfm": "SURVEY 8f row 3: the point-only BA iteration of pipelines/BA.py:117-151 (surface projection, SDF at the projected points, "
+              "se3 -> SE3 per observation, robust reprojection loss, L1 sdf + eikonal; forward + backward) on 4096 tracked points, "
+              "shipped DTU SDF network, replayed as one CUDA graph",
 }
 METRIC = "rendered rays/sec (fwd+bwd, 4096-ray batch)"
 
@@ -320,6 +323,8 @@ def run_forward_only(args):
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     clocks = ClockSampler(0)
+    if args.workload == "ba_sfm":
+        return run_ba_sfm(args, opt, sdf, dev, peak, clocks, W)
     if args.workload == "image":
         H, Wd = opt.data.image_size
         rot, pos = synthetic.look_at_cameras(1, 1.0, torch.Generator().manual_seed(0))
@@ -371,6 +376,71 @@ def run_forward_only(args):
             "roofline": {"bound": "hbm", "kernel": "field_forward", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "algorithmic_bytes_per_unit": per_unit,
                          "note": "whole step (all launches), algorithmic bytes = gather + per-sample outputs"}}
+    print(json.dumps(line))
+
+
+def run_ba_sfm(args, opt, sdf, dev, peak, clocks, W):
+    from levels2fm_b200 import ba, ops, parallel
+    from levels2fm_b200.graph import GraphedStep
+    n = 4096
+    g = torch.Generator().manual_seed(0)
+    xyz = torch.nn.Parameter((torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) * (0.5 + 0.02 * torch.randn(n, 1, generator=g))).to(dev))
+    se3 = torch.nn.Parameter(torch.tensor([[0.05, -0.1, 0.02, 0.05, -0.03, 2.5], [-0.2, 0.3, 0.1, -0.1, 0.02, 2.6]], device=dev))
+    pose_idx = (torch.arange(n) % 2).to(dev)
+    intr = torch.tensor([[1920.0, 0.0, 800.0], [0.0, 1920.0, 600.0], [0.0, 0.0, 1.0]], device=dev)
+    kp_h = (torch.rand(n, 2, generator=g) * torch.tensor([1600.0, 1200.0])).pin_memory()
+    kp = kp_h.to(dev)
+    bucket = parallel.GradBucket(list(sdf.parameters()) + [xyz, se3])
+    thr = 2.0 / 10 / 100
+
+    def iteration(kp_in):
+        bucket.zero()
+        t = ba.surface_ba_terms(sdf, xyz, se3, pose_idx, intr, kp_in, thr)
+        loss = t["reproj_loss"] + 100.0 * t["sdf_surf"] + 100.0 * t["eikonal_loss"]        # 10 ** loss_weight.ba (options/LevelS2fM.yaml:113-118)
+        loss.backward()
+        return loss.detach()
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn(kp)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / steps, out
+    for _ in range(W):
+        iteration(kp)
+    torch.cuda.synchronize()
+    ops.KLOG.reset()
+    eager_ms, _ = timed(iteration, args.steps)
+    launches_per_it = ops.KLOG.total() // args.steps
+    step = GraphedStep(iteration, (kp,))
+    for _ in range(W):
+        step(kp)
+    clocks.start()
+    graph_ms, loss = timed(step, args.steps)
+    clk = clocks.stop()
+    host = torch.empty(1).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host.copy_(step(kp_h.to(dev, non_blocking=True)).reshape(1), non_blocking=True)
+    torch.cuda.synchronize()
+    e2e = n * args.steps / (time.perf_counter() - t0)
+    per_pt = 2 * (2 * GRID_BYTES_PER_EVAL) + 64          # two field evaluations, each gathered and scattered once
+    achieved = n * per_pt / (graph_ms * 1e-3) / 1e9
+    line = {"metric": "BA sfm tracked points/sec (fwd+bwd, 4096 points per iteration)", "value": n / (graph_ms * 1e-3), "unit": "points/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": W, "ms_per_step": graph_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": FORWARD_ONLY["ba_sfm"], "points_per_iteration": n, "cuda_graph": True,
+                       "eager_ms_per_iteration": eager_ms, "graph_speedup": eager_ms / graph_ms, "launches_per_iteration": launches_per_it,
+                       "l2": "the iteration is launch / latency bound (4096 points): no L2 flush"},
+            "clocks": clk, "gpu_launches": launches_per_it * args.steps, "loss": float(loss),
+            "e2e": {"value": e2e, "unit": "points/s", "h2d_bytes_per_step": int(kp_h.numel() * 4), "d2h_bytes_per_step": 4},
+            "roofline": {"bound": "hbm", "kernel": "whole iteration", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "algorithmic_bytes_per_unit": per_pt,
+                         "note": "launch-bound by construction: 4096 points are 0.3 % of one C2 render batch"}}
     print(json.dumps(line))
 
 

@@ -328,6 +328,15 @@ int ls2fm_se3_to_SE3_backward(const float* wu, int64_t n, const float* g_Rt, flo
 int ls2fm_generate_rays_backward(const float* pose, const float* kinv, const float* xy, int32_t n_cams, int64_t n_pix,
                                  const float* g_center, const float* g_ray, float* d_pose, void* stream);
 
+/* ------------------------------------------------------------------ BA "sfm" reprojection residual
+ * pipelines/BA.py:126-141 for n tracked points, each with its own world->camera pose Rt [n,3,4] (BA.py:127) and shared
+ * intrinsics K [3,3]: (a,b,c) = K (R x + t), uv = (a,b) / (c + eps), d = |uv - kypts|, rows kept where |sdf| < sdf_band and uv is
+ * finite; loss = 0.5 mean(2 log(1 + d^2/4)) + 0.5 mean(d) over the kept rows.
+ * sums [4] (zeroed by the call): sum 2 log(1 + d^2/4), sum d, kept rows, mask_surf rows.  uv [n,2], mask_surf [n] u8, and the
+ * gradients of the loss g_xyz [n,3], g_Rt [n,3,4] are written when non-NULL.  Two launches, no host synchronisation. */
+int ls2fm_reproj_loss(const float* xyz, const float* Rt, const float* K, const float* kypts, const float* sdf, int64_t n, float sdf_band,
+                      float eps, float* sums, float* uv, uint8_t* mask_surf, float* g_xyz, float* g_Rt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

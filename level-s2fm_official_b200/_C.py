@@ -103,6 +103,7 @@ SIGNATURES = {
     "ls2fm_generate_rays_backward": (C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_int64, _VP, _VP, _VP, _VP]),
     "ls2fm_se3_to_SE3": (C.c_int, [_VP, C.c_int64, _VP, _VP]),
     "ls2fm_se3_to_SE3_backward": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP]),
+    "ls2fm_reproj_loss": (C.c_int, [_VP] * 5 + [C.c_int64, C.c_float, C.c_float] + [_VP] * 6),
     "ls2fm_sphere_trace": (C.c_int, [C.POINTER(Field), _VP, _VP, C.c_int64, C.c_float, C.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_sample_error_bounded": (C.c_int, [C.POINTER(Field), _VP, C.POINTER(SamplerCfg), _VP, _VP, C.c_int32, _VP, _VP, _VP, _VP, _VP]),
 }

@@ -672,6 +672,24 @@ int ls2fm_se3_to_SE3_backward(const float* wu, int64_t n, const float* g_Rt, flo
     return ls_check_launch("se3_to_SE3_backward");
 }
 
+int ls2fm_reproj_loss(const float* xyz, const float* Rt, const float* K, const float* kypts, const float* sdf, int64_t n, float sdf_band,
+                      float eps, float* sums, float* uv, uint8_t* mask_surf, float* g_xyz, float* g_Rt, void* stream) {
+    if (n < 0 || !sums) return ls_fail("reproj_loss: bad arguments");
+    if (n > 0 && (!xyz || !Rt || !K || !kypts || !sdf)) return ls_fail("reproj_loss: NULL input");
+    ls_memset_async(sums, 0, 4 * sizeof(float), stream);
+    if (n == 0) return 0;
+    const int bs = 128;
+    int64_t grid = (n + bs - 1) / bs;
+    if (grid > 4 * ls_sm_count()) grid = 4 * ls_sm_count();
+    LS_LAUNCH(ls_reproj_sums_kernel, (unsigned)grid, bs, 0, stream, xyz, Rt, K, kypts, sdf, n, sdf_band, eps, sums, uv, mask_surf);
+    if (ls_check_launch("reproj_loss(sums)")) return 1;
+    if (g_xyz || g_Rt) {
+        LS_LAUNCH(ls_reproj_grads_kernel, (unsigned)grid, bs, 0, stream, xyz, Rt, K, kypts, sdf, n, sdf_band, eps, sums, g_xyz, g_Rt);
+        return ls_check_launch("reproj_loss(grads)");
+    }
+    return 0;
+}
+
 int ls2fm_generate_rays(const float* pose, const float* kinv, const float* xy, int32_t n_cams, int64_t n_pix, float* center, float* ray,
                         void* stream) {
     if (n_cams < 0 || n_pix < 0) return ls_fail("generate_rays: bad sizes");

@@ -802,3 +802,36 @@ class Se3ToSE3(torch.autograd.Function):
         _call(lib, "se3_to_SE3_backward", lib.dll.ls2fm_se3_to_SE3_backward, lib.ptr(w), w.shape[0], lib.ptr(g.reshape(-1, 12).contiguous().float()),
               lib.ptr(d), lib.stream())
         return d.view(ctx.shape)
+
+
+class ReprojLoss(torch.autograd.Function):
+    """The reprojection term of the BA "sfm" loop (pipelines/BA.py:126-141) in two launches, gradients included.
+    forward(xyz [n,3], Rt [n,3,4], K [3,3], kypts [n,2], sdf [n] or [n,1], sdf_band, eps=1e-6)
+        -> (loss, uv [n,2], mask_surf [n] bool, n_kept);  loss is 0 when no point lies in the band (BA.py:147-148)."""
+
+    @staticmethod
+    def forward(ctx, xyz, Rt, K, kypts, sdf, sdf_band, eps=1e-6):
+        lib = _C.get()
+        x, P = xyz.detach().reshape(-1, 3).contiguous().float(), Rt.detach().reshape(-1, 12).contiguous().float()
+        Kc, kp = K.detach().reshape(9).contiguous().float(), kypts.detach().reshape(-1, 2).contiguous().float()
+        s = sdf.detach().reshape(-1).contiguous().float()
+        n = x.shape[0]
+        dev = x.device
+        sums = torch.empty(4, device=dev)
+        uv = torch.empty(n, 2, device=dev)
+        mask = torch.empty(n, dtype=torch.uint8, device=dev)
+        g_x, g_P = torch.empty_like(x), torch.empty_like(P)
+        _call(lib, "reproj_loss", lib.dll.ls2fm_reproj_loss, lib.ptr(x), lib.ptr(P), lib.ptr(Kc), lib.ptr(kp), lib.ptr(s), n, float(sdf_band),
+              float(eps), lib.ptr(sums), lib.ptr(uv), lib.ptr(mask, torch.uint8), lib.ptr(g_x), lib.ptr(g_P), lib.stream(), launches=2)
+        ctx.save_for_backward(g_x, g_P)
+        ctx.shapes = (xyz.shape, Rt.shape)
+        nk = sums[2]
+        loss = torch.where(nk > 0, 0.5 * (sums[0] + sums[1]) / nk.clamp_min(1.0), torch.zeros((), device=dev))
+        ctx.mark_non_differentiable(uv, mask, nk)
+        return loss, uv, mask.bool(), nk
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        g_x, g_P = ctx.saved_tensors
+        sx, sP = ctx.shapes
+        return (g_x * g_loss).view(sx), (g_P * g_loss).view(sP), None, None, None, None, None

@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE -- see oracle/__init__.py.  Runs /root/reference's own model
 oracle/ref_shim.py (third-party tcnn / vren ops replaced by oracle/hashgrid.py / oracle/aabb.py) on seeded inputs
 and stores inputs, outputs and gradients.  The fixtures pin (a) oracle/port.py and (b) the CUDA path.
 
-    python -m oracle.make_golden            # rewrites tests/golden/c1_render.npz, c2_sampler.npz, st_dtu.npz
+    python -m oracle.make_golden            # rewrites tests/golden/c1_render.npz, c2_sampler.npz, c2_sampler_hard.npz, st_dtu.npz
 """
 from __future__ import annotations
 
@@ -115,8 +115,29 @@ def c2_sampler():
     print("c2_sampler: t", tuple(t.shape), "iters", iters.unique().tolist())
 
 
+def c2_sampler_hard():
+    """The reference's error-bounded sampler where it struggles: a tight eps, few samples, a rough field -- several up-sampling
+    rounds, the bisection on beta+ (models/Renderer.py:281-291) and rays that NEVER converge (iters = -1, Renderer.py:309-321),
+    plus rays that miss the box.  Pins oracle/port.volsdf_sampling's bisection / give-up path against the reference itself."""
+    L, R, N = 16, 48, 16
+    opt = ref_shim.make_opt("DTU", **{"SDF.VolSDF.sample_intvs": N, "SDF.VolSDF.final_sample_intvs": 24, "SDF.VolSDF.volsdf_sampling": True,
+                                      "SDF.VolSDF.eps": 0.002, "SDF.VolSDF.max_upsample_iter": 4})
+    ref_shim.apply_c2_fixes(opt)
+    sdf, rad, ren = ref_shim.build_models(opt)
+    cfg = port.SceneCfg(n_levels=L, sample_intvs=N, final_sample_intvs=24, volsdf_sampling=True, eps=0.002, max_upsample_iter=4)
+    sdf_sd, _ = port.random_state(cfg, seed=8, table_std=0.05, generic_weights=False, hash_weight_std=0.1)
+    _load(sdf, sdf_sd)
+    center, ray = _rays(1, R, 1.0, seed=21)
+    center[0, :3] += 10                       # rays that miss the box
+    with torch.no_grad():
+        t, beta_plus, iters = ren.volsdf_sampling(opt, center, ray, SDF_Field=sdf)
+    d = {"center": center, "ray": ray, "t": t, "beta_plus": beta_plus, "iters": iters}
+    np.savez_compressed(os.path.join(OUT, "c2_sampler_hard.npz"), **{k: v.numpy() for k, v in d.items()})
+    print("c2_sampler_hard: t", tuple(t.shape), "iters", {int(k): int((iters == k).sum()) for k in iters.unique()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["c1_render", "st_dtu", "c2_sampler"]
+    which = sys.argv[1:] or ["c1_render", "st_dtu", "c2_sampler", "c2_sampler_hard"]
     for w in which:
         globals()[w]()

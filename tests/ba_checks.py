@@ -1,0 +1,75 @@
+"""levels2fm_b200.ba.surface_ba_terms against a line-by-line torch restatement of
+/root/reference/pipelines/BA.py:123-148 + compute_loss's "sfm" branch (BA.py:199-203) on the oracle field."""
+import torch
+
+from oracle import port
+
+from . import common
+
+
+def reference_terms(xyzs, se3, pose_idx, intr, kp, sdf_sd, cfg, sdf_threshold, epsilon=1e-6):
+    xyzs_new, normals_value = port.get_surface_pts(xyzs, sdf_sd, cfg)                        # BA.py:124
+    sdfs = port.infer_sdf(xyzs_new, sdf_sd, cfg).view(-1, 1)                                # BA.py:125
+    poses_forward = port.se3_to_SE3(se3[pose_idx])                                          # BA.py:127
+    X = xyzs_new.unsqueeze(1)
+    X_hom = torch.cat([X, torch.ones_like(X[..., :1])], dim=-1)                             # utils/camera.py:199-207
+    xyzx_forward = X_hom @ poses_forward.transpose(-1, -2)
+    uvs = xyzx_forward @ intr.repeat(xyzx_forward.shape[0], 1, 1).transpose(-1, -2)
+    uvs = (uvs / (uvs[..., 2:] + epsilon))[..., :2].squeeze(1)                              # BA.py:131
+    mask_surf = abs(sdfs) < 2 * sdf_threshold
+    inf_mask = torch.isinf(uvs)
+    inf_mask = ((inf_mask[mask_surf.squeeze()][:, 0]) | (inf_mask[mask_surf.squeeze()][:, 1]))
+    d = torch.norm(uvs - kp, dim=-1)[mask_surf.squeeze()][~inf_mask]
+    reproj = 0.5 * ((2 * torch.log(1 + d ** 2 / 4)).mean()) + 0.5 * d.mean()                # BA.py:136-140
+    if mask_surf.sum() == 0:
+        reproj = torch.zeros(())
+    return {"xyzs_new": xyzs_new, "sdfs": sdfs, "gradients": normals_value, "uvs": uvs, "mask_surf": mask_surf.squeeze(-1),
+            "reproj_loss": reproj, "sdf_surf": sdfs.abs().mean(), "eikonal_loss": (normals_value - 1).abs().mean()}
+
+
+def ba_terms_case(device, n=60, dataset="DTU", band_scale=40.0):
+    from levels2fm_b200 import ba
+    opt = common.make_opt(dataset, device, 16, (None, 64, 16), 16)
+    cfg = common.cfg_of(opt, 16)
+    sdf_sd, _ = port.random_state(cfg, seed=5, table_std=0.02, generic_weights=False, hash_weight_std=0.02)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    for k in sdf_sd:
+        sdf_sd[k] = sdf_sd[k].clone().requires_grad_(True)
+    half = float(cfg.bound_max[0])
+    g = torch.Generator().manual_seed(2)
+    xyz0 = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) * 0.5 * half * (1 + 0.05 * torch.randn(n, 1, generator=g))
+    se30 = torch.tensor([[0.05, -0.1, 0.02, 0.05 * half, -0.03 * half, 2.5 * half], [-0.2, 0.3, 0.1, -0.1 * half, 0.02 * half, 2.6 * half]])
+    pose_idx = torch.arange(n) % 2
+    intr = torch.tensor([[600.0, 0.0, 320.0], [0.0, 600.0, 240.0], [0.0, 0.0, 1.0]])
+    kp = torch.rand(n, 2, generator=g) * torch.tensor([640.0, 480.0])
+    # (the reference's band is 2 * (bmax - bmin) / 10 / Res = 4e-3 * half; wider here so that part -- not all -- of the points fall inside)
+    thr = band_scale * 2 * half / 10 / 100 / 2
+    w = (1.0, 100.0, 100.0)                                                                   # 10 ** loss_weight.ba of reproj / sdf_surf / eikonal
+    res = {}
+    for who in ("ours", "ref"):
+        dev = device if who == "ours" else "cpu"
+        xyz, se3 = xyz0.clone().to(dev).requires_grad_(True), se30.clone().to(dev).requires_grad_(True)
+        if who == "ours":
+            t = ba.surface_ba_terms(sdf, xyz, se3, pose_idx.to(dev), intr.to(dev), kp.to(dev), thr)
+        else:
+            t = reference_terms(xyz, se3, pose_idx, intr, kp, sdf_sd, cfg, thr)
+        loss = w[0] * t["reproj_loss"] + w[1] * t["sdf_surf"] + w[2] * t["eikonal_loss"]
+        loss.backward()
+        res[who] = (t, loss.detach().cpu(), xyz.grad.cpu(), se3.grad.cpu())
+    to, tr = res["ours"][0], res["ref"][0]
+    assert 0.2 < tr["mask_surf"].float().mean().item() < 0.98
+    assert torch.equal(to["mask_surf"].cpu(), tr["mask_surf"])
+    for k in ("reproj_loss", "sdf_surf", "eikonal_loss"):
+        a, b = float(to[k].detach()), float(tr[k].detach())
+        assert abs(a - b) <= 1e-4 * abs(b), (k, a, b)
+    assert common.rel_err(to["uvs"].detach().cpu(), tr["uvs"].detach()) < 1e-4
+    assert common.cosine(res["ours"][2], res["ref"][2]) > 1 - 1e-6 and common.rel_err(res["ours"][2], res["ref"][2]) < 2e-3
+    assert common.cosine(res["ours"][3], res["ref"][3]) > 1 - 1e-6 and common.rel_err(res["ours"][3], res["ref"][3]) < 2e-3
+    for k, p in sdf.named_parameters():
+        if sdf_sd[k].grad is None:
+            continue
+        assert common.cosine(p.grad.cpu(), sdf_sd[k].grad) > 1 - 1e-6, (k, common.cosine(p.grad.cpu(), sdf_sd[k].grad))
+    # no point in the band: the reference sets the term to 0 (BA.py:147-148)
+    t0 = ba.surface_ba_terms(sdf, xyz0.to(device) * 0.2, se30.to(device), pose_idx.to(device), intr.to(device), kp.to(device), 1e-9)
+    assert float(t0["reproj_loss"].detach()) == 0.0 and not bool(t0["mask_surf"].any())

@@ -434,3 +434,48 @@ def test_fused_loss_tail_matches_reference_tail(eik_masked, none_finished):
 
 def test_se3_to_SE3_kernel_matches_oracle():
     gc.se3_case(DEV, n=5000)
+
+
+@pytest.mark.parametrize("dataset", ["DTU", "ETH3D"])
+def test_ba_surface_terms_match_reference_block(dataset):
+    from . import ba_checks
+    ba_checks.ba_terms_case(DEV, n=3000, dataset=dataset)
+
+
+def test_ba_surface_iteration_replays_as_cuda_graph():
+    """The point-only BA iteration (forward + backward into a gradient bucket) has no host synchronisation: captured once,
+    replayed, same gradients as the eager run."""
+    from levels2fm_b200 import ba, parallel
+    from levels2fm_b200.graph import GraphedStep
+    opt = common.make_opt("DTU", DEV, 16, (None, 64, 16), 16)
+    cfg = common.cfg_of(opt, 16)
+    sdf_sd, _ = port.random_state(cfg, seed=5, table_std=0.02, generic_weights=False, hash_weight_std=0.02)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    n = 2000
+    g = torch.Generator().manual_seed(2)
+    xyz = torch.nn.Parameter((torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1) * 0.5).to(DEV))
+    se3 = torch.nn.Parameter(torch.tensor([[0.05, -0.1, 0.02, 0.05, -0.03, 2.5], [-0.2, 0.3, 0.1, -0.1, 0.02, 2.6]], device=DEV))
+    pose_idx = (torch.arange(n) % 2).to(DEV)
+    intr = torch.tensor([[600.0, 0.0, 320.0], [0.0, 600.0, 240.0], [0.0, 0.0, 1.0]], device=DEV)
+    kp = (torch.rand(n, 2, generator=g) * torch.tensor([640.0, 480.0])).to(DEV)
+    bucket = parallel.GradBucket(list(sdf.parameters()) + [xyz, se3])
+
+    def iteration(kp_in):
+        bucket.zero()
+        t = ba.surface_ba_terms(sdf, xyz, se3, pose_idx, intr, kp_in, 0.04)
+        loss = t["reproj_loss"] + 100.0 * t["sdf_surf"] + 100.0 * t["eikonal_loss"]
+        loss.backward()
+        return loss.detach()
+    eager_loss = iteration(kp).clone()
+    eager = bucket.flat.clone()
+    step = GraphedStep(iteration, (kp,))
+    for _ in range(3):
+        graph_loss = step(kp)
+    torch.cuda.synchronize()
+    assert abs(float(graph_loss) - float(eager_loss)) < 1e-5 * abs(float(eager_loss))
+    assert common.cosine(bucket.flat.cpu(), eager.cpu()) > 1 - 1e-6
+
+
+def test_error_bounded_sampler_against_reference_hard_case_golden():
+    gc.sampler_golden_hard_case(DEV)

@@ -342,3 +342,12 @@ def test_gradient_bucket_direct_scatter_equals_autograd_accumulation():
 
 def test_se3_to_SE3_kernel_matches_oracle():
     gc.se3_case("cpu")
+
+
+def test_ba_surface_terms_match_reference_block():
+    from . import ba_checks
+    ba_checks.ba_terms_case("cpu", n=40)
+
+
+def test_error_bounded_sampler_against_reference_hard_case_golden():
+    gc.sampler_golden_hard_case("cpu")

@@ -126,6 +126,19 @@ def test_port_matches_reference_golden_sampler():
     gc.assert_close(out["depth_mlp"], gold["out.depth_mlp"], what="c2 depth")
 
 
+def test_port_matches_reference_golden_sampler_hard_case():
+    """The bisection on beta+ and the give-up path (iters = -1) of the port against the reference's own run of
+    models/Renderer.py:281-321 (fixture: oracle/make_golden.c2_sampler_hard, 40 of 48 rays never converge)."""
+    gold = gc.load("c2_sampler_hard.npz")
+    cfg = port.SceneCfg(n_levels=16, sample_intvs=16, final_sample_intvs=24, volsdf_sampling=True, eps=0.002, max_upsample_iter=4)
+    sdf_sd, _ = port.random_state(cfg, seed=8, table_std=0.05, generic_weights=False, hash_weight_std=0.1)
+    t, beta_plus, iters = port.volsdf_sampling(gold["center"], gold["ray"], sdf_sd, cfg)
+    assert (gold["iters"] == -1).sum() >= 30 and (gold["iters"] >= 0).sum() >= 5
+    assert torch.equal(iters, gold["iters"])
+    gc.assert_close(t, gold["t"], tol=1e-5, what="hard sampler t")
+    gc.assert_close(beta_plus, gold["beta_plus"], tol=1e-5, what="hard sampler beta plus")
+
+
 def test_renderer_api_compat_pieces_match_the_oracle():
     """Renderer.composite / error_bound / sample_pdf stay callable with the reference's semantics (pure tensor math)."""
     from levels2fm_b200.models.Renderer import Renderer
