@@ -410,8 +410,10 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
     // ---- tensor-core kernel: needs the operand image (weights stream from it), the 2-channel form (normals carry gradient),
     //      chunk-aligned level groups and matrices that fit a ring slot; everything else runs the fp32-SIMT kernel below
     //      Launches below LS_BT_MIN_SAMPLES stay on the SIMT kernel: a few tiles do not amortise the tensor-core kernel's set-up.
-    const bool tc_ok = tan && field->tc_image && (field->n_levels & 3) == 0 && !want_dx;
-    if (mode == 2 && !tc_ok) return ls_fail("field_backward_tc: needs field.tc_image, a gradient on the normals, n_levels % 4 == 0 and no position gradients");
+    // (a launch without a gradient on the normals -- RadF.Geo_enc under dual_field: g_y only -- runs the same kernel with a zero
+    //  tangent channel: every second-order term vanishes identically, and it is still faster than the fp32-SIMT first-order kernel)
+    const bool tc_ok = field->tc_image && (field->n_levels & 3) == 0 && !want_dx && (tan || g_y || g_sdf);
+    if (mode == 2 && !tc_ok) return ls_fail("field_backward_tc: needs field.tc_image, an upstream gradient, n_levels % 4 == 0 and no position gradients");
     if ((mode == 2 || (mode == 0 && pts->n >= LS_BT_MIN_SAMPLES)) && tc_ok) {
         const LsTcNet img = ls_plan_tc(*field, with_rad ? rad->in_dim : 0);
         const LsBtNet net = ls_plan_bt(*field, with_rad ? rad->in_dim : 0);

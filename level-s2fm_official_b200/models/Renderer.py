@@ -95,9 +95,11 @@ class Renderer:
         t2 = t.reshape(B * R, N)
         geo2 = None
         if Rad_Field.dual_field:
-            _, geo2, _, _ = ops.FieldEval.apply(Rad_Field.field_spec(), None, Rad_Field.embed_fn.embedder_obj.params,
-                                                Rad_Field.Geo_enc.theta(), None, None, None, None, c2, r2, t2, 0, None,
-                                                True, False)
+            theta2 = Rad_Field.Geo_enc.theta()
+            table2 = Rad_Field.embed_fn.embedder_obj.params
+            image2 = ops.field_prepare_raw(_C.get(), Rad_Field.field_spec(), table2.detach(), theta2.detach().contiguous(), None)
+            _, geo2, _, _ = ops.FieldEval.apply(Rad_Field.field_spec(), None, table2, theta2, None, None, None, None, c2, r2, t2, 0, None,
+                                                True, False, image2)
         sdf, _, nrm, rgbs = ops.FieldEval.apply(SDF_Field.field_spec(), Rad_Field.rad_spec(), SDF_Field.table(),
                                                 prepared["theta"], prepared["w_eff"], prepared["b_eff"], geo2, None, c2, r2, t2,
                                                 0, None, False, True, prepared["image"])

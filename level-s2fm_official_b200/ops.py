@@ -243,8 +243,8 @@ def field_backward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: 
         ig.d_xyz, ig.d_center, ig.d_ray, ig.d_t = lib.ptr(d_xyz), lib.ptr(d_center), lib.ptr(d_ray), lib.ptr(d_t)
         if mode == "tc":
             mode = "auto"   # position gradients come from the fp32-SIMT kernel
-    if mode == "tc" and (image is None or (g_nrm is None and g_rgb is None)):
-        mode = "auto"       # no operand image / no gradient on the normals: nothing for the tensor-core kernel to do
+    if mode == "tc" and image is None:
+        mode = "auto"       # no operand image: the tensor-core kernel has no weights to stream
     name = {"auto": "field_backward", "simt": "field_backward_simt", "tc": "field_backward_tc"}[mode]
     _call(lib, name, getattr(lib.dll, "ls2fm_" + name), f, pts, rad, lib.ptr(g_y), lib.ptr(g_sdf), lib.ptr(g_nrm), lib.ptr(g_rgb), lib.ptr(saved_nrm), lib.ptr(saved_rgb),
         lib.ptr(d_table), lib.ptr(d_theta), lib.ptr(d_w_eff), lib.ptr(d_b_eff), lib.ptr(d_geo2), ig, lib.stream(), units=int(pts.n))
