@@ -88,3 +88,20 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
                 assert "hostsim import" not in txt and "from tests" not in txt, fn
+
+
+def test_new_entry_points_validate_arguments(lib):
+    """Round-2 entry points: NULL / out-of-range arguments are reported through the error string, empty inputs are no-ops
+    (host-side checks only: nothing is launched without a GPU)."""
+    d = lib.dll
+    assert d.ls2fm_se3_to_SE3(None, 0, None, None) == 0
+    assert d.ls2fm_se3_to_SE3(None, 3, None, None) != 0 and b"se3_to_SE3" in d.ls2fm_last_error()
+    assert d.ls2fm_se3_to_SE3_backward(None, 2, None, None, None) != 0
+    org = (C.c_double * 3)(0.0, 0.0, 0.0)
+    assert d.ls2fm_grid_points(8, 0.1, org, 0, 0, None, None) == 0
+    assert d.ls2fm_grid_points(8, 0.1, org, 500, 100, None, None) != 0 and b"grid_points" in d.ls2fm_last_error()
+    assert d.ls2fm_grid_points(1, 0.1, org, 0, 1, None, None) != 0
+    assert d.ls2fm_reproj_loss(None, None, None, None, None, 5, 0.1, 1e-6, None, None, None, None, None, None) != 0
+    assert b"reproj_loss" in d.ls2fm_last_error()
+    assert d.ls2fm_render_tail(None, None, None, None, None, None, 4, 8, 1, 1.0, 1.0, 1.0, None, None, None, None, None, None, None, None) != 0
+    assert b"render_tail" in d.ls2fm_last_error()

@@ -479,3 +479,21 @@ def test_ba_surface_iteration_replays_as_cuda_graph():
 
 def test_error_bounded_sampler_against_reference_hard_case_golden():
     gc.sampler_golden_hard_case(DEV)
+
+
+def test_large_single_launch_values_only():
+    """One values-only launch of 2 097 152 points (16 384 tiles, > 100 per SM): spot-checked against the oracle, and equal to the
+    same points evaluated in small chunks (index arithmetic of the persistent two-tiles-in-flight kernel)."""
+    opt = common.make_opt("DTU", DEV, 16, (None, 64, 16), 16)
+    cfg = common.cfg_of(opt, 16)
+    sdf_sd, _ = port.random_state(cfg, seed=8, table_std=0.2)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    vol = sdf.infer_sdf_grid(N=128, volume_size=2.0, chunk=1 << 22)            # a single 2 M-point launch
+    vol2 = sdf.infer_sdf_grid(N=128, volume_size=2.0, chunk=50000)             # 42 launches with a ragged tail
+    assert torch.equal(vol, vol2)
+    from .inference_checks import reference_grid_points
+    pts = reference_grid_points(128, 2.0)
+    idx = torch.randperm(128 ** 3, generator=torch.Generator().manual_seed(0))[:5000]
+    ref = port.infer_sdf(pts[idx], sdf_sd, cfg).reshape(-1)
+    assert common.rel_err(vol.reshape(-1)[idx.to(DEV)].cpu(), ref.detach()) < 1e-4
