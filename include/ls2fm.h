@@ -130,6 +130,15 @@ int ls2fm_grid_encode(const ls2fm_field_t* field, const float* u, int64_t m,
 int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64_t m,
                                const float* g_enc, float* d_table, float* d_u, void* stream);
 
+/* second-order pieces (tcnn's encoding is double-differentiable and the reference uses it: SDF.gradient, models/SDF.py:102-114,
+ * differentiates through the encoding's input gradient with create_graph=True).  v [m,3] = the direction arriving at d_u:
+ *   t_enc [m, 2L] (written)  = J_enc(u) v               -- gradient of d_u w.r.t. g_enc
+ *   d_table (+=)             = scatter((dw/du . v) g_enc) -- gradient of d_u w.r.t. the table
+ *   d_u2 [m,3] (+=)          = mixed second derivatives of the trilinear weights along v, contracted with table . g_enc
+ * each output nullable (d_table / d_u2 need g_enc). */
+int ls2fm_grid_encode_tangent(const ls2fm_field_t* field, const float* u, int64_t m, const float* v, const float* g_enc,
+                              float* t_enc, float* d_table, float* d_u2, void* stream);
+
 /* ------------------------------------------------------------------ parameter preparation
  * One weight-normed linear layer as the reference stores it (nn.utils.weight_norm, models/base.py:200,241):
  * W = g * v / ||v||_row.  dg / dv / db are the backward outputs (written, same shapes); ignored by the forward. */

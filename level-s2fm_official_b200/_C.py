@@ -82,6 +82,7 @@ SIGNATURES = {
     "ls2fm_ray_aabb": (C.c_int, [_VP, _VP, C.c_int64, _F3, _F3, _VP, _VP, _VP]),
     "ls2fm_grid_encode": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP]),
     "ls2fm_grid_encode_backward": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    "ls2fm_grid_encode_tangent": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_params_forward": (C.c_int, [C.POINTER(ParamLayer), C.c_int32, C.POINTER(ParamLayer), _VP, _VP, _VP, _VP]),
     "ls2fm_params_backward": (C.c_int, [C.POINTER(ParamLayer), C.c_int32, C.POINTER(ParamLayer), _VP, _VP, _VP, C.c_int32, _VP]),
     "ls2fm_field_image_floats": (C.c_int64, [C.POINTER(Field), C.POINTER(Radiance)]),

@@ -218,6 +218,19 @@ int ls2fm_grid_encode_backward(const ls2fm_field_t* field, const float* u, int64
     return ls_check_launch("grid_encode_backward");
 }
 
+int ls2fm_grid_encode_tangent(const ls2fm_field_t* field, const float* u, int64_t m, const float* v, const float* g_enc, float* t_enc,
+                              float* d_table, float* d_u2, void* stream) {
+    if (!field || !field->table) return ls_fail("grid_encode_tangent: field/table is NULL");
+    if (field->n_levels < 1 || field->n_levels > LS2FM_MAX_LEVELS) return ls_fail("grid_encode_tangent: n_levels out of range");
+    if (m < 0 || (m > 0 && (!u || !v))) return ls_fail("grid_encode_tangent: bad arguments");
+    if ((d_table || d_u2) && !g_enc) return ls_fail("grid_encode_tangent: d_table / d_u2 need g_enc");
+    if (m == 0) return 0;
+    const int bs = 256;
+    const int64_t total = m * field->n_levels;
+    LS_LAUNCH(ls_grid_encode_tangent_kernel, (unsigned)((total + bs - 1) / bs), bs, 0, stream, *field, u, m, v, g_enc, t_enc, d_table, d_u2);
+    return ls_check_launch("grid_encode_tangent");
+}
+
 static int ls_fill_params(LsParamArgs& a, const ls2fm_param_layer_t* geo, int32_t n_geo, const ls2fm_param_layer_t* rad, bool backward) {
     memset(&a, 0, sizeof(a));
     if (n_geo < 0 || n_geo > LS2FM_MAX_LAYERS || (n_geo > 0 && !geo)) return ls_fail("params: bad geometry layer list");

@@ -301,6 +301,57 @@ __global__ void ls_grid_encode_backward_kernel(const ls2fm_field_t f, const floa
     }
 }
 
+// second-order pieces of the stand-alone encoding (what makes ops.GridEncode double-differentiable, as tcnn's encoding is: the
+// reference's SDF.gradient differentiates THROUGH the encoding's input gradient with create_graph=True, models/SDF.py:102-114).
+// With v = an upstream direction on u (the gradient arriving at d_u) and dw_c = sum_d v_d * d(w_c)/d(u_d):
+//   t_enc [m, 2L]  = sum_c dw_c * table[c]              (tangent of the encoding along v: gradient w.r.t. g_enc)
+//   d_table       += dw_c * g_enc                        (gradient of d_u w.r.t. the table)
+//   d_u2 [m,3]    += sum_c (mixed second derivative of w_c along v) * (table[c] . g_enc)     (gradient of d_u w.r.t. u; a trilinear
+//                     cell has no pure second derivatives)
+// each output nullable; g_enc may be NULL when only t_enc is wanted.
+__global__ void ls_grid_encode_tangent_kernel(const ls2fm_field_t f, const float* __restrict__ u, int64_t m,
+                                              const float* __restrict__ v, const float* __restrict__ g_enc,
+                                              float* __restrict__ t_enc, float* __restrict__ d_table, float* __restrict__ d_u2) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int L = f.n_levels;
+    if (gid >= m * L) return;
+    const int64_t i = gid / L;
+    const int l = (int)(gid - i * L);
+    const float uu[3] = {u[3 * i], u[3 * i + 1], u[3 * i + 2]};
+    const float scale = f.levels[l].scale;
+    const uint32_t res = f.levels[l].resolution, size = f.levels[l].size, hashed = f.levels[l].hashed, off = f.levels[l].offset;
+    const LsCell c = ls_cell(scale, uu);
+    const float vs[3] = {v[3 * i] * scale, v[3 * i + 1] * scale, v[3 * i + 2] * scale};
+    float g0 = 0.f, g1 = 0.f;
+    if (g_enc) { g0 = g_enc[i * 2 * L + 2 * l]; g1 = g_enc[i * 2 * L + 2 * l + 1]; }
+    float t0 = 0.f, t1 = 0.f, du[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t idx = ls_corner_index(res, size, hashed, c, k);
+        const float fk[3] = {(k & 1) ? c.w[0] : 1.f - c.w[0], (k & 2) ? c.w[1] : 1.f - c.w[1], (k & 4) ? c.w[2] : 1.f - c.w[2]};
+        const float sg[3] = {(k & 1) ? 1.f : -1.f, (k & 2) ? 1.f : -1.f, (k & 4) ? 1.f : -1.f};
+        const float dw = sg[0] * vs[0] * fk[1] * fk[2] + sg[1] * vs[1] * fk[0] * fk[2] + sg[2] * vs[2] * fk[0] * fk[1];
+        const float2 tv = __ldg(reinterpret_cast<const float2*>(f.table) + off + idx);
+        t0 = fmaf(dw, tv.x, t0);
+        t1 = fmaf(dw, tv.y, t1);
+        if (d_table && g_enc) atomicAdd(reinterpret_cast<float2*>(d_table) + off + idx, make_float2(dw * g0, dw * g1));
+        if (d_u2 && g_enc) {
+            const float gv = g0 * tv.x + g1 * tv.y;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const int d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+                du[d] += sg[d] * (sg[d1] * vs[d1] * fk[d2] + sg[d2] * vs[d2] * fk[d1]) * gv;
+            }
+        }
+    }
+    if (t_enc) { t_enc[i * 2 * L + 2 * l] = t0; t_enc[i * 2 * L + 2 * l + 1] = t1; }
+    if (d_u2 && g_enc) {
+        atomicAdd(d_u2 + 3 * i, scale * du[0]);
+        atomicAdd(d_u2 + 3 * i + 1, scale * du[1]);
+        atomicAdd(d_u2 + 3 * i + 2, scale * du[2]);
+    }
+}
+
 // ---------------------------------------------------------------- marching-cubes query grid
 // The N^3 query points of utils/util.py:392-411 (extract_mesh), generated on the device instead of in numpy + one H2D copy per
 // 16 k chunk.  Reproduces the reference's float64 arithmetic term by term -- including its true division: the y / x grid

@@ -538,26 +538,80 @@ class UniformDepths(torch.autograd.Function):
         return d_c, d_r, None, None, None
 
 
+def grid_encode_tangent_raw(lib, grid: GridSpec, table, u, v, g_enc=None, want_t_enc=True, d_table=None, d_u2=None):
+    m = u.numel() // 3
+    spec = FieldSpec(grid, (0, 0, 0), (1, 1, 1), [3 + 2 * grid.n_levels, 64, 1])
+    f = spec.c_field(lib, table, None)
+    t_enc = torch.empty(m, grid.n_output_dims, device=u.device) if want_t_enc else None
+    _call(lib, "grid_encode_tangent", lib.dll.ls2fm_grid_encode_tangent, f, lib.ptr(u), m, lib.ptr(v), lib.ptr(g_enc), lib.ptr(t_enc),
+          lib.ptr(d_table), lib.ptr(d_u2), lib.stream())
+    return t_enc
+
+
 class GridEncode(torch.autograd.Function):
-    """``tcnn.Encoding`` replacement (models/base.py:17,37): u [M,3] -> [M, L*F]; grads to the table and to u."""
+    """``tcnn.Encoding`` replacement (models/base.py:17,37): u [M,3] -> [M, L*F]; gradients to the table and to u, and -- like
+    tcnn's -- differentiable a second time (``GridEncodeBackward``): the reference's ``SDF.gradient`` back-propagates THROUGH the
+    input gradient of the encoding (create_graph=True, models/SDF.py:102-114)."""
 
     @staticmethod
     def forward(ctx, grid, table, u):
         lib = _C.get()
-        table, u = table.detach().contiguous(), u.detach().contiguous()
-        enc, _ = grid_encode_raw(lib, grid, table, u)
+        enc, _ = grid_encode_raw(lib, grid, table.detach().contiguous(), u.detach().contiguous())
         ctx.grid = grid
         ctx.save_for_backward(table, u)
         return enc
 
     @staticmethod
     def backward(ctx, g_enc):
-        lib = _C.get()
         table, u = ctx.saved_tensors
-        d_table = torch.zeros_like(table) if ctx.needs_input_grad[1] else None
-        d_u = torch.zeros_like(u) if ctx.needs_input_grad[2] else None
-        grid_encode_backward_raw(lib, ctx.grid, table, u, g_enc.contiguous(), d_table, d_u)
-        return None, d_table, d_u
+        d_table, d_u = GridEncodeBackward.apply(ctx.grid, table, u, g_enc, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return None, d_table if ctx.needs_input_grad[1] else None, d_u if ctx.needs_input_grad[2] else None
+
+
+class GridEncodeBackward(torch.autograd.Function):
+    """(table, u, g_enc) -> (d_table, d_u) of GridEncode, itself differentiable:
+       d(d_table)/d(g_enc) and d(d_u)/d(g_enc) : encode(gg_table, u) + J_enc(table, u) gg_u
+       d(d_u)/d(table)                          : the tangent scatter along gg_u
+       d(d_table)/d(u), d(d_u)/d(u)             : J_enc(gg_table, u)^T g_enc + the mixed second derivatives along gg_u."""
+
+    @staticmethod
+    def forward(ctx, grid, table, u, g_enc, want_table, want_u):
+        lib = _C.get()
+        t_c, u_c, g_c = table.detach().contiguous(), u.detach().contiguous(), g_enc.detach().contiguous()
+        d_table = torch.zeros_like(t_c) if want_table else None
+        d_u = torch.zeros_like(u_c) if want_u else None
+        grid_encode_backward_raw(lib, grid, t_c, u_c, g_c, d_table, d_u)
+        ctx.grid = grid
+        ctx.save_for_backward(t_c, u_c, g_c)
+        outs = (d_table if want_table else t_c.new_empty(0), d_u if want_u else t_c.new_empty(0))
+        ctx.mark_non_differentiable(*[o for o in outs if o.numel() == 0])
+        return outs
+
+    @staticmethod
+    def backward(ctx, gg_table, gg_u):
+        lib = _C.get()
+        table, u, g_enc = ctx.saved_tensors
+        grid = ctx.grid
+        need_t, need_u, need_g = ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        have_t = gg_table is not None and gg_table.numel() > 0
+        have_u = gg_u is not None and gg_u.numel() > 0
+        d_g = d_t = d_uu = None
+        if need_g:
+            d_g = torch.zeros_like(g_enc)
+            if have_t:
+                d_g = d_g + grid_encode_raw(lib, grid, gg_table.detach().contiguous(), u)[0]
+            if have_u:
+                d_g = d_g + grid_encode_tangent_raw(lib, grid, table, u, gg_u.detach().contiguous())
+        if need_t and have_u:
+            d_t = torch.zeros_like(table)
+            grid_encode_tangent_raw(lib, grid, table, u, gg_u.detach().contiguous(), g_enc, want_t_enc=False, d_table=d_t)
+        if need_u:
+            d_uu = torch.zeros_like(u)
+            if have_t:
+                grid_encode_backward_raw(lib, grid, gg_table.detach().contiguous(), u, g_enc, None, d_uu)
+            if have_u:
+                grid_encode_tangent_raw(lib, grid, table, u, gg_u.detach().contiguous(), g_enc, want_t_enc=False, d_u2=d_uu)
+        return None, d_t, d_uu, d_g, None, None
 
 
 def sample_error_bounded_raw(lib, spec: FieldSpec, table, theta, beta_param, center, ray, n_samples, n_final,

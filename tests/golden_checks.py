@@ -359,3 +359,30 @@ def se3_case(device, n=50, seed=0):
     assert_close(w.grad[:2, 3:], w_ref.grad[:2, 3:], tol=1e-5, what="se3_to_SE3 translation gradient at theta = 0")
     # batched leading shape
     assert rays_mod.se3_to_SE3(wu.view(5, n // 5, 6).to(device)).shape == (5, n // 5, 3, 4)
+
+
+def grid_encode_double_backward_case(device, m=200, n_levels=16):
+    """ops.GridEncode (the tcnn.Encoding stand-in of seam B) is differentiable twice, like tcnn's encoding: gradients of a function
+    of d enc / d u w.r.t. the table, the points and the upstream weights, against the oracle's autograd-built hash grid."""
+    from levels2fm_b200 import ops
+    from oracle import hashgrid
+    cfg = port.SceneCfg(n_levels=n_levels)
+    meta = cfg.grid()
+    grid = ops.GridSpec(n_levels, 2, 19, 16, cfg.per_level_scale).resolve()
+    g = torch.Generator().manual_seed(0)
+    table0 = torch.randn(meta.n_params, generator=g) * 0.3
+    u0 = torch.rand(m, 3, generator=g) * 0.9 + 0.05
+    w0 = torch.randn(2 * n_levels, generator=g)
+    c0 = torch.randn(m, 3, generator=g)
+    res = {}
+    for who in ("ours", "ref"):
+        dev = device if who == "ours" else "cpu"
+        table, u, w = (t.clone().to(dev).requires_grad_(True) for t in (table0, u0, w0))
+        enc = ops.GridEncode.apply(grid, table, u) if who == "ours" else hashgrid.encode(u, table, meta)
+        y = (torch.tanh(enc) * w).sum()
+        (g_u,) = torch.autograd.grad(y, u, create_graph=True)
+        z = (g_u * c0.to(dev)).sum() + 0.1 * (g_u ** 2).sum()
+        res[who] = [t.cpu() for t in torch.autograd.grad(z, [table, u, w])] + [g_u.detach().cpu()]
+    for name, a, b in zip(("d/d table", "d/d u", "d/d w", "first-order d_u"), res["ours"], res["ref"]):
+        assert common.cosine(a, b) > 1 - 1e-6, (name, common.cosine(a, b))
+        assert common.rel_err(a, b) < 2e-3, (name, common.rel_err(a, b))

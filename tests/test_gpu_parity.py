@@ -497,3 +497,7 @@ def test_large_single_launch_values_only():
     idx = torch.randperm(128 ** 3, generator=torch.Generator().manual_seed(0))[:5000]
     ref = port.infer_sdf(pts[idx], sdf_sd, cfg).reshape(-1)
     assert common.rel_err(vol.reshape(-1)[idx.to(DEV)].cpu(), ref.detach()) < 1e-4
+
+
+def test_standalone_grid_encoding_is_double_differentiable():
+    gc.grid_encode_double_backward_case(DEV, m=5000)

@@ -356,3 +356,7 @@ def test_ba_surface_terms_match_reference_block():
 
 def test_error_bounded_sampler_against_reference_hard_case_golden():
     gc.sampler_golden_hard_case("cpu")
+
+
+def test_standalone_grid_encoding_is_double_differentiable():
+    gc.grid_encode_double_backward_case("cpu", m=120)
