@@ -204,7 +204,12 @@ typedef struct {
     float* d_center;
     float* d_ray;
     float* d_t;
+    float* workspace;   /* device, nullable: ls2fm_field_backward_workspace_floats(n) floats of scratch.  With it, launches that qualify
+                           for the tcgen05 backward kernel keep running on it: the kernel parks the per-sample encoding adjoints
+                           (72 floats / sample) here and a light second kernel gathers the table once more and contracts them into the
+                           position gradient.  Without it such launches run the fp32-SIMT kernel (2.6x slower at 4096 x 128 samples). */
 } ls2fm_input_grads_t;
+int64_t ls2fm_field_backward_workspace_floats(int64_t n_samples);
 
 /* backward of ls2fm_field_forward.  Upstream gradients (all nullable): g_y [n,dout], g_sdf [n],
  * g_nrm [n,3], g_rgb [n,3].  saved_nrm/saved_rgb: forward outputs (required when rad != NULL).

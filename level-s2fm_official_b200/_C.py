@@ -66,7 +66,7 @@ class Radiance(C.Structure):
 
 
 class InputGrads(C.Structure):
-    _fields_ = [("d_xyz", C.c_void_p), ("d_center", C.c_void_p), ("d_ray", C.c_void_p), ("d_t", C.c_void_p)]
+    _fields_ = [("d_xyz", C.c_void_p), ("d_center", C.c_void_p), ("d_ray", C.c_void_p), ("d_t", C.c_void_p), ("workspace", C.c_void_p)]
 
 
 _F3 = C.c_float * 3
@@ -90,6 +90,7 @@ SIGNATURES = {
     "ls2fm_field_forward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_field_forward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance), _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_field_forward_ws": (C.c_int, [C.POINTER(Field), C.POINTER(Points), _VP, _VP, _VP]),
+    "ls2fm_field_backward_workspace_floats": (C.c_int64, [C.c_int64]),
     "ls2fm_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 11 + [C.POINTER(InputGrads), _VP]),
     "ls2fm_field_backward_simt": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 11 + [C.POINTER(InputGrads), _VP]),
     "ls2fm_field_backward_tc": (C.c_int, [C.POINTER(Field), C.POINTER(Points), C.POINTER(Radiance)] + [_VP] * 11 + [C.POINTER(InputGrads), _VP]),

@@ -425,8 +425,10 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
     //      Launches below LS_BT_MIN_SAMPLES stay on the SIMT kernel: a few tiles do not amortise the tensor-core kernel's set-up.
     // (a launch without a gradient on the normals -- RadF.Geo_enc under dual_field: g_y only -- runs the same kernel with a zero
     //  tangent channel: every second-order term vanishes identically, and it is still faster than the fp32-SIMT first-order kernel)
-    const bool tc_ok = field->tc_image && (field->n_levels & 3) == 0 && !want_dx && (tan || g_y || g_sdf);
-    if (mode == 2 && !tc_ok) return ls_fail("field_backward_tc: needs field.tc_image, an upstream gradient, n_levels % 4 == 0 and no position gradients");
+    //  position gradients: the tensor-core kernel parks the encoding adjoints in ig.workspace and ls_field_posgrad_kernel finishes)
+    const bool tc_ok = field->tc_image && (field->n_levels & 3) == 0 && (!want_dx || a.ig.workspace) && (tan || g_y || g_sdf);
+    if (!want_dx) a.ig.workspace = nullptr;
+    if (mode == 2 && !tc_ok) return ls_fail("field_backward_tc: needs field.tc_image, an upstream gradient, n_levels % 4 == 0 and (for position gradients) a workspace");
     if ((mode == 2 || (mode == 0 && pts->n >= LS_BT_MIN_SAMPLES)) && tc_ok) {
         const LsTcNet img = ls_plan_tc(*field, with_rad ? rad->in_dim : 0);
         const LsBtNet net = ls_plan_bt(*field, with_rad ? rad->in_dim : 0);
@@ -445,10 +447,18 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
             } while (0)
             if (KL == 2) LS_BT_LAUNCH(2); else if (KL == 3) LS_BT_LAUNCH(3); else LS_BT_LAUNCH(4);
 #undef LS_BT_LAUNCH
-            return ls_check_launch("field_backward(tc)");
+            if (ls_check_launch("field_backward(tc)")) return 1;
+            if (want_dx) {
+                int64_t pg = (pts->n + 255) / 256;
+                if (pg > 8 * ls_sm_count()) pg = 8 * ls_sm_count();
+                LS_LAUNCH(ls_field_posgrad_kernel, (unsigned)pg, 256, 0, stream, a);
+                return ls_check_launch("field_backward(posgrad)");
+            }
+            return 0;
         }
         if (mode == 2) return ls_fail("field_backward_tc: the network does not fit the tensor-core kernel");
     }
+    a.ig.workspace = nullptr;       // (the fp32-SIMT kernel computes the position gradient itself)
     a.net = ls_plan_net(*field, with_rad ? rad->in_dim : 0, LS_BW_WARPS, true);
     const int smem = a.net.total * (int)sizeof(float);
     if (smem > ls_max_smem()) return ls_fail("field_backward: network does not fit in shared memory");
@@ -464,6 +474,8 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
 #undef LS_BW_LAUNCH
     return ls_check_launch("field_backward");
 }
+
+int64_t ls2fm_field_backward_workspace_floats(int64_t n_samples) { return n_samples < 0 ? -1 : n_samples * (int64_t)LS_PG_PITCH; }
 
 int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts, const ls2fm_radiance_t* rad, const float* g_y,
                          const float* g_sdf, const float* g_nrm, const float* g_rgb, const float* saved_nrm,

@@ -127,6 +127,142 @@ LS_DEV void ls_bt_wgrad(uint32_t tmem, int d_col, const float* a_raw, const floa
 #endif
 }
 
+// ================================================================ position gradients behind the tensor-core backward
+// The tensor-core kernel has the adjoints of the encoding (ebar: primal channel, ebar_dot: tangent channel) in registers at the end of
+// a tile but no registers left for another table gather; it parks them in a workspace (LS_PG_PITCH floats per sample:
+// [0,32) ebar of the hash features, [32,64) ebar_dot, [64,67) ebar of x / rescale) and this kernel -- one thread per sample, 64 warps
+// per SM, memory-bound like the stand-alone encoding -- gathers the table once more and contracts:
+//   dL/dx = Je^T ebar + (d(Je nbar)/dx)^T ebar_dot + W_eff[:,0:3]^T pbar      (+ the Fourier-embedding term for d_ray)
+// Same arithmetic as phase B6 of ls_field_backward_kernel.  Ray mode: the 32 samples of a warp usually belong to one ray, so the
+// warp reduces first and issues one atomic per component.
+constexpr int LS_PG_PITCH = 72;
+__global__ void __launch_bounds__(256) ls_field_posgrad_kernel(const LsFieldArgs a) {
+    const float* ws = a.ig.workspace;
+    const int L = a.f.n_levels;
+    const bool rad = a.r.w_eff != nullptr && a.g_rgb != nullptr;
+    const int in_dim = a.r.in_dim, nf = a.r.n_freq;
+    const int o_ray = 6;
+    const int64_t n_pad = (a.p.n + 31) / 32 * 32;
+    for (int64_t i_in = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i_in < n_pad; i_in += (int64_t)gridDim.x * blockDim.x) {
+        const bool valid = i_in < a.p.n;
+        float x[3] = {0.f, 0.f, 0.f}, u[3];
+        int ray_id = 0;
+        int64_t i = i_in;
+        if (valid) ls_sample_point(a.p, i_in, x, &ray_id, &i);
+        ls_world_to_unit(a.f.bound_min, a.f.bound_max, x, u);
+        float pbar[3] = {0.f, 0.f, 0.f}, nbar[3] = {0.f, 0.f, 0.f}, dx[3] = {0.f, 0.f, 0.f}, dirg[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+            if (rad) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float rgb = __ldg(a.saved_rgb + 3 * i + c);
+                    pbar[c] = __ldg(a.g_rgb + 3 * i + c) * rgb * (1.f - rgb);
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                float v = a.g_nrm ? __ldg(a.g_nrm + 3 * i + d) : 0.f;
+                if (rad) v += __ldg(a.r.w_eff + 3 + d) * pbar[0] + __ldg(a.r.w_eff + in_dim + 3 + d) * pbar[1] + __ldg(a.r.w_eff + 2 * in_dim + 3 + d) * pbar[2];
+                nbar[d] = v;
+            }
+            const float* w = ws + i * LS_PG_PITCH;
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
+                const float scale = a.f.levels[l].scale;
+                const uint32_t res = a.f.levels[l].resolution, size = a.f.levels[l].size, hashed = a.f.levels[l].hashed;
+                const float2* vt = reinterpret_cast<const float2*>(a.f.table) + a.f.levels[l].offset;
+                const LsCell c = ls_cell(scale, u);
+                uint32_t ci[8];
+                ls_corner_indices<0, 8>(res, size, hashed, c, ci);
+                float2 tv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) tv[k] = __ldg(vt + ci[k]);
+                const float e0 = w[2 * l], e1 = w[2 * l + 1], t0 = w[32 + 2 * l], t1 = w[32 + 2 * l + 1];
+                float ns[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) ns[d] = nbar[d] * scale * a.inv_ext[d];
+                float lx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float fk[3] = {(k & 1) ? c.w[0] : 1.f - c.w[0], (k & 2) ? c.w[1] : 1.f - c.w[1], (k & 4) ? c.w[2] : 1.f - c.w[2]};
+                    const float sg3[3] = {(k & 1) ? 1.f : -1.f, (k & 2) ? 1.f : -1.f, (k & 4) ? 1.f : -1.f};
+                    const float Ak = tv[k].x * e0 + tv[k].y * e1, Bk = tv[k].x * t0 + tv[k].y * t1;
+                    lx[0] += sg3[0] * (fk[1] * fk[2] * Ak + (sg3[1] * ns[1] * fk[2] + sg3[2] * ns[2] * fk[1]) * Bk);
+                    lx[1] += sg3[1] * (fk[2] * fk[0] * Ak + (sg3[2] * ns[2] * fk[0] + sg3[0] * ns[0] * fk[2]) * Bk);
+                    lx[2] += sg3[2] * (fk[0] * fk[1] * Ak + (sg3[0] * ns[0] * fk[1] + sg3[1] * ns[1] * fk[0]) * Bk);
+                }
+#pragma unroll
+                for (int d = 0; d < 3; ++d) dx[d] += lx[d] * scale * a.inv_ext[d];
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                dx[d] += w[64 + d] / a.f.rescale;
+                if (rad) dx[d] += __ldg(a.r.w_eff + d) * pbar[0] + __ldg(a.r.w_eff + in_dim + d) * pbar[1] + __ldg(a.r.w_eff + 2 * in_dim + d) * pbar[2];
+            }
+            if (rad && a.ig.d_ray) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const float dv = __ldg(a.p.ray + 3 * ray_id + d);
+                    for (int c = 0; c < 3; ++c) {
+                        float acc = __ldg(a.r.w_eff + c * in_dim + o_ray + d);
+                        for (int k = 0; k < nf; ++k) {
+                            const float fr = (float)(1 << k);
+                            acc += fr * (__ldg(a.r.w_eff + c * in_dim + o_ray + 3 + 6 * k + d) * cosf(dv * fr) -
+                                         __ldg(a.r.w_eff + c * in_dim + o_ray + 6 + 6 * k + d) * sinf(dv * fr));
+                        }
+                        dirg[d] += acc * pbar[c];
+                    }
+                }
+            }
+        }
+        if (a.p.xyz) {
+            if (valid && a.ig.d_xyz) { a.ig.d_xyz[3 * i] = dx[0]; a.ig.d_xyz[3 * i + 1] = dx[1]; a.ig.d_xyz[3 * i + 2] = dx[2]; }
+            if (valid && a.ig.d_ray && rad) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) atomicAdd(a.ig.d_ray + 3 * ray_id + d, dirg[d]);
+            }
+        } else {
+            float tv = 0.f;
+            if (valid) {
+                const int j = (int)(i_in - (int64_t)ray_id * a.p.n_per_ray);
+                tv = __ldg(a.p.t + (int64_t)ray_id * a.p.t_stride + a.p.t_offset + j);
+                if (a.ig.d_t) {
+                    float dt = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) dt += __ldg(a.p.ray + 3 * ray_id + d) * dx[d];
+                    a.ig.d_t[i_in] = dt;
+                }
+            }
+            // one ray per warp (the common case: n_per_ray a multiple of 32): reduce first, one atomic per component
+            const int r0 = __shfl_sync(0xffffffffu, ray_id, 0);
+            const bool uniform = __all_sync(0xffffffffu, !valid || ray_id == r0) && __shfl_sync(0xffffffffu, valid ? 1 : 0, 0);
+            float acc[6] = {dx[0], dx[1], dx[2], tv * dx[0] + dirg[0], tv * dx[1] + dirg[1], tv * dx[2] + dirg[2]};
+            if (uniform) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    float v = valid ? acc[q] : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    acc[q] = v;
+                }
+                if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        if (a.ig.d_center) atomicAdd(a.ig.d_center + 3 * r0 + d, acc[d]);
+                        if (a.ig.d_ray) atomicAdd(a.ig.d_ray + 3 * r0 + d, acc[3 + d]);
+                    }
+                }
+            } else if (valid) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    if (a.ig.d_center) atomicAdd(a.ig.d_center + 3 * ray_id + d, acc[d]);
+                    if (a.ig.d_ray) atomicAdd(a.ig.d_ray + 3 * ray_id + d, acc[3 + d]);
+                }
+            }
+        }
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(const LsFieldArgs a, const LsTcNet img, const LsBtNet net) {
     LS_DYN_SMEM(smem);
@@ -686,12 +822,22 @@ __global__ void __launch_bounds__(LS_BT_THREADS, 1) ls_field_backward_tc_kernel(
         if (has_levels) {
             float c8[8];
             ls_tmem_ld(tmem, LS_BT_D + 8 * cg, c8, 8);
+            if (a.ig.workspace && valid) {      // position gradients wanted: park the adjoints for ls_field_posgrad_kernel
+                float* w = a.ig.workspace + i * LS_PG_PITCH + (isT ? 32 : 0) + 8 * cg;
+                ls_st4(w, make_float4(c8[0], c8[1], c8[2], c8[3]));
+                ls_st4(w + 4, make_float4(c8[4], c8[5], c8[6], c8[7]));
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float r = __shfl_xor_sync(0xffffffffu, isT ? c8[k] : c8[4 + k], 16);
                 sb[k] = isT ? r : c8[k];            // adjoint of the features of my levels
                 sd[k] = isT ? c8[4 + k] : r;        // adjoint of their tangents
             }
+        }
+        if (a.ig.workspace && cg == 0) {             // ... and the adjoint of the x / rescale columns (primal rows; the TMEM load is
+            float cx[8];                             //     warp-collective, so the whole warp executes it)
+            ls_tmem_ld(tmem, LS_BT_D + nh, cx, 8);
+            if (valid && !isT) ls_st4(a.ig.workspace + i * LS_PG_PITCH + 64, make_float4(cx[0], cx[1], cx[2], 0.f));
         }
         sc_pending = true;
         { const int o = pb_prev; pb_prev = pb_cur; pb_cur = pb_nxt; pb_nxt = o; }

@@ -57,8 +57,13 @@ class SDF(nn.Module):
         field parameters AND the positions (like tcnn's encoding in the reference)."""
         shp = xyz.shape[:-1]
         flat = xyz.reshape(-1, 3).float()
-        sdf, y, nrm, _ = ops.FieldEval.apply(self.field_spec(), None, self.table(), self.SDF_MLP.theta(), None, None, None,
-                                             flat, None, None, None, 0, None, want_y, want_nrm, None, sdf_x_detached)
+        theta = self.SDF_MLP.theta()
+        image = None
+        if flat.shape[0] >= ops.TC_BACKWARD_MIN_SAMPLES:      # large point sets: tensor-core operand image (streamed weights, tcgen05 backward)
+            from .. import _C
+            image = ops.field_prepare_raw(_C.get(), self.field_spec(), self.table().detach(), theta.detach().contiguous(), None)
+        sdf, y, nrm, _ = ops.FieldEval.apply(self.field_spec(), None, self.table(), theta, None, None, None,
+                                             flat, None, None, None, 0, None, want_y, want_nrm, image, sdf_x_detached)
         sdf = sdf.view(*shp, 1)
         nrm = nrm.view(*shp, 3) if want_nrm else None
         if self._bg_sdf():

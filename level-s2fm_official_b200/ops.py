@@ -241,8 +241,10 @@ def field_backward_raw(lib, spec: FieldSpec, table, theta, pts: _C.Points, rad: 
     if d_xyz is not None or d_center is not None or d_ray is not None or d_t is not None:
         ig = _C.InputGrads()
         ig.d_xyz, ig.d_center, ig.d_ray, ig.d_t = lib.ptr(d_xyz), lib.ptr(d_center), lib.ptr(d_ray), lib.ptr(d_t)
-        if mode == "tc":
-            mode = "auto"   # position gradients come from the fp32-SIMT kernel
+        if image is not None and mode != "simt" and (mode == "tc" or int(pts.n) >= TC_BACKWARD_MIN_SAMPLES):
+            # scratch for the tensor-core route (encoding adjoints parked per sample, finished by ls_field_posgrad_kernel)
+            ws = torch.empty(int(lib.dll.ls2fm_field_backward_workspace_floats(int(pts.n))), device=table.device)
+            ig.workspace = lib.ptr(ws)
     if mode == "tc" and image is None:
         mode = "auto"       # no operand image: the tensor-core kernel has no weights to stream
     name = {"auto": "field_backward", "simt": "field_backward_simt", "tc": "field_backward_tc"}[mode]
@@ -315,6 +317,7 @@ def composite_backward_raw(lib, ray, t, sdf, rgbs, nrm, beta_param, beta_speed, 
 
 
 # ------------------------------------------------------------------------- autograd
+TC_BACKWARD_MIN_SAMPLES = 8192     # LS_BT_MIN_SAMPLES of the library's automatic dispatch
 FORWARD_WS = False         # tests set this to route values-only evaluations through the experimental warp-specialised kernel
 BACKWARD_MODE = "auto"     # tests set "simt" / "tc" to cross-check the tensor-core backward kernel against the fp32-SIMT one
 

@@ -16,6 +16,11 @@ from oracle import port
 from . import common
 
 
+def _lib():
+    from levels2fm_b200 import _C
+    return _C.get()
+
+
 def _scene(device, dataset="DTU", n_levels=16, layers=(None, 64, 64, 16), n_samples=16, dual=False, seed=4):
     opt = common.make_opt(dataset, device, n_levels, layers, n_samples, dual)
     cfg = common.cfg_of(opt, n_levels)
@@ -230,3 +235,41 @@ def radf_geometry_feat_input_grad(device, n=100):
     f = port.field_out(xr, rad_sd["embed_fn.embedder_obj.params"], port.mlp_from_sd(rad_sd, "Geo_enc.mlp", cfg.n_sdf_layers), cfg)
     (f * w).sum().backward()
     assert common.rel_err(x.grad.cpu(), xr.grad) < 1e-4 and common.cosine(x.grad.cpu(), xr.grad) > 1 - 1e-6
+
+
+def tensor_core_route_matches_simt_route(device, n_rays=70, n_samples=33, dataset="DTU", dual=False):
+    """Position gradients behind the tcgen05 backward kernel (adjoints parked in a workspace + ls_field_posgrad_kernel) against
+    the fp32-SIMT kernel's own B6 phase: d_center / d_ray through a whole render iteration, and d_xyz of explicit points."""
+    from levels2fm_b200 import ops
+    opt, cfg, sdf_sd, rad_sd, sdf, rad, ren = _scene(device, dataset=dataset, layers=(None, 64, 64, 16) if not dual else (None, 64, 16),
+                                                     n_samples=n_samples, dual=dual)
+    half = float(opt.data.bound_max[0])
+    center, ray = common.make_rays(1, n_rays, half, device=device)
+    g = torch.Generator().manual_seed(0)
+    x0 = (torch.rand(n_rays * 3 + 1, 3, generator=g) * 1.2 - 0.6) * half
+    gw = None
+    res = {}
+    for mode in ("simt", "tc"):
+        ops.BACKWARD_MODE = mode
+        try:
+            for p in list(sdf.parameters()) + list(rad.parameters()):
+                p.grad = None
+            c, r = center.clone().requires_grad_(True), ray.clone().requires_grad_(True)
+            out = ren.forward(opt, c, r, sdf, rad)
+            if gw is None:
+                gw = {k: torch.randn(out[k].shape, generator=g).to(device) for k in ["rgb", "depth_mlp", "normal_mlp", "sdfs_volume"]}
+            common.loss_fn(out, gw).backward()
+            # explicit points straight through the op, with the operand image (so that "tc" really takes the tensor-core route)
+            x = x0.clone().to(device).requires_grad_(True)
+            theta = sdf.SDF_MLP.theta()
+            image = ops.field_prepare_raw(_lib(), sdf.field_spec(), sdf.table().detach(), theta.detach().contiguous(), None)
+            s, f, nrm, _ = ops.FieldEval.apply(sdf.field_spec(), None, sdf.table(), theta, None, None, None, x, None, None, None, 0, None,
+                                               True, True, image)
+            (gx,) = torch.autograd.grad(s.sum() + (f ** 2).sum() + (nrm.norm(dim=-1) - 1).abs().sum(), x)
+            res[mode] = (c.grad.cpu(), r.grad.cpu(), gx.cpu(), sdf.table().grad.cpu().clone())
+        finally:
+            ops.BACKWARD_MODE = "auto"
+    for name, a, b in zip(("d_center", "d_ray", "d_xyz", "d_table"), res["tc"], res["simt"]):
+        assert float(b.abs().max()) > 0, name
+        assert common.cosine(a, b) > 1 - 1e-7, (name, common.cosine(a, b))
+        assert common.rel_err(a, b) < 2e-4, (name, common.rel_err(a, b))

@@ -501,3 +501,9 @@ def test_large_single_launch_values_only():
 
 def test_standalone_grid_encoding_is_double_differentiable():
     gc.grid_encode_double_backward_case(DEV, m=5000)
+
+
+@pytest.mark.parametrize("dataset,dual,n_rays,n_samples", [("DTU", False, 300, 128), ("bmvs", True, 70, 47), ("ETH3D", False, 1, 33)])
+def test_position_gradients_on_the_tensor_core_route(dataset, dual, n_rays, n_samples):
+    from . import input_grad_checks as ig
+    ig.tensor_core_route_matches_simt_route(DEV, n_rays=n_rays, n_samples=n_samples, dataset=dataset, dual=dual)

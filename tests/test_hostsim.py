@@ -360,3 +360,9 @@ def test_error_bounded_sampler_against_reference_hard_case_golden():
 
 def test_standalone_grid_encoding_is_double_differentiable():
     gc.grid_encode_double_backward_case("cpu", m=120)
+
+
+@pytest.mark.parametrize("dataset,dual", [("DTU", False), ("bmvs", True)])
+def test_position_gradients_on_the_tensor_core_route(dataset, dual):
+    from . import input_grad_checks as ig
+    ig.tensor_core_route_matches_simt_route("cpu", n_rays=9, n_samples=15, dataset=dataset, dual=dual)
