@@ -120,6 +120,13 @@ int ls2fm_ray_aabb(const float* rays_o, const float* rays_d, int64_t m,
                    const float center[3], const float half_size[3],
                    float* hits_t, int32_t* hit_cnt, void* stream);
 
+/* The backward the reference's RayAABBIntersector lacks (utils/custom_functions.py:10-31; SURVEY 8a defect iii): on the slab axis that
+ * decides t_near / t_far, dt/do_k = -1/d_k and dt/dd_k = -t/d_k; zero where t_near was clamped to 0 or the ray misses.
+ * n_samples > 0: g [R, n_samples] is the gradient on the uniform depths of ls2fm_sample_uniform; n_samples == 0: g [R,2] is the
+ * gradient on hits_t itself.  hits_t [R,2] as returned by the forward.  d_center / d_ray [R,3] are written. */
+int ls2fm_ray_aabb_backward(const float* center, const float* ray, int32_t n_rays, int32_t n_samples, const float bound_min[3],
+                            const float bound_max[3], const float* hits_t, const float* g, float* d_center, float* d_ray, void* stream);
+
 /* ------------------------------------------------------------------ tcnn replacement (unfused)
  * replaces tcnn.Encoding.forward (models/base.py:37): u [m,3] -> enc [m, 2*n_levels].
  * idx (nullable) [m, n_levels, 8] uint32 receives the table entry index of every corner

@@ -80,6 +80,7 @@ SIGNATURES = {
     "ls2fm_grid_meta": (C.c_int, [C.POINTER(GridCfg), C.POINTER(Level), C.POINTER(C.c_uint32)]),
     "ls2fm_smem_bytes": (C.c_int, [C.POINTER(Field), C.c_int, C.c_int]),
     "ls2fm_ray_aabb": (C.c_int, [_VP, _VP, C.c_int64, _F3, _F3, _VP, _VP, _VP]),
+    "ls2fm_ray_aabb_backward": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _F3, _F3, _VP, _VP, _VP, _VP, _VP]),
     "ls2fm_grid_encode": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP]),
     "ls2fm_grid_encode_backward": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP, _VP]),
     "ls2fm_grid_encode_tangent": (C.c_int, [C.POINTER(Field), _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP]),

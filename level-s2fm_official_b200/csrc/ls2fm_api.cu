@@ -195,6 +195,19 @@ int ls2fm_sample_uniform(const float* center, const float* ray, int32_t n_rays, 
     return ls_check_launch("sample_uniform");
 }
 
+int ls2fm_ray_aabb_backward(const float* center, const float* ray, int32_t n_rays, int32_t n_samples, const float bound_min[3],
+                            const float bound_max[3], const float* hits_t, const float* g, float* d_center, float* d_ray, void* stream) {
+    if (n_rays < 0 || n_samples < 0) return ls_fail("ray_aabb_backward: bad sizes");
+    if (n_rays > 0 && (!center || !ray || !hits_t || !g || !d_center || !d_ray)) return ls_fail("ray_aabb_backward: NULL argument");
+    if (n_rays == 0) return 0;
+    float c[3], h[3];
+    for (int d = 0; d < 3; ++d) { c[d] = (bound_max[d] + bound_min[d]) / 2.f; h[d] = (bound_max[d] - bound_min[d]) / 2.f; }
+    const int wpb = 8;
+    LS_LAUNCH(ls_aabb_vjp_kernel, (unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, 0, stream, center, ray, n_rays, n_samples, c[0], c[1], c[2],
+              h[0], h[1], h[2], hits_t, g, d_center, d_ray);
+    return ls_check_launch("ray_aabb_backward");
+}
+
 int ls2fm_grid_encode(const ls2fm_field_t* field, const float* u, int64_t m, float* enc, uint32_t* idx, void* stream) {
     if (!field || !field->table) return ls_fail("grid_encode: field/table is NULL");
     if (field->n_levels < 1 || field->n_levels > LS2FM_MAX_LEVELS) return ls_fail("grid_encode: n_levels out of range");

@@ -45,6 +45,59 @@ __global__ void ls_sample_uniform_kernel(const float* __restrict__ center, const
         t[(int64_t)r * n_samples + i] = ls_fadd(ls_fmul(ls_fdiv((float)i + 0.5f, (float)n_samples), ext), tn);
 }
 
+// ---------------------------------------------------------------- slab-test VJP (SURVEY 8a defect iii)
+// The reference's RayAABBIntersector defines no backward (utils/custom_functions.py:10-31).  On the slab axis k that decides t_near
+// (the arg-max of the per-axis entry depths) and on the one that decides t_far (the arg-min of the exit depths):
+//   dt/do_k = -1/d_k,   dt/dd_k = -t/d_k;   zero where t_near was clamped to 0 or the ray misses the box.
+// One warp per ray.  Upstream: g_t [R,N] on the uniform depths t_i = (i + 0.5)/N (t_far - t_near) + t_near (n_samples > 0), or
+// g_hits [R,2] on (t_near, t_far) directly (n_samples == 0).  d_center / d_ray [R,3] are WRITTEN.
+__global__ void ls_aabb_vjp_kernel(const float* __restrict__ center, const float* __restrict__ ray, int n_rays, int n_samples,
+                                   float cx, float cy, float cz, float hx, float hy, float hz, const float* __restrict__ hits,
+                                   const float* __restrict__ g, float* __restrict__ d_center, float* __restrict__ d_ray) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_rays) return;
+    const int r = warp;
+    float g_near = 0.f, g_far = 0.f;
+    if (n_samples > 0) {
+        for (int i = lane; i < n_samples; i += 32) {
+            const float gi = g[(int64_t)r * n_samples + i];
+            const float fr = ((float)i + 0.5f) / (float)n_samples;
+            g_far += gi * fr;
+            g_near += gi * (1.f - fr);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            g_near += __shfl_xor_sync(0xffffffffu, g_near, o);
+            g_far += __shfl_xor_sync(0xffffffffu, g_far, o);
+        }
+    } else {
+        g_near = g[2 * r];
+        g_far = g[2 * r + 1];
+    }
+    if (lane != 0) return;
+    const float o[3] = {center[3 * r], center[3 * r + 1], center[3 * r + 2]};
+    const float d[3] = {ray[3 * r], ray[3 * r + 1], ray[3 * r + 2]};
+    const float c[3] = {cx, cy, cz}, h[3] = {hx, hy, hz};
+    const float tn = hits[2 * r], tf = hits[2 * r + 1];
+    int k_near = 0, k_far = 0;
+    float best_lo = -INFINITY, best_hi = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {       // same arithmetic as ls_ray_aabb, first arg-max / arg-min like torch
+        const float inv = ls_fdiv(1.0f, d[k]);
+        const float lo = ls_fmul(ls_fsub(ls_fsub(c[k], h[k]), o[k]), inv);
+        const float hi = ls_fmul(ls_fsub(ls_fadd(c[k], h[k]), o[k]), inv);
+        const float mn = fminf(lo, hi), mx = fmaxf(lo, hi);
+        if (mn > best_lo) { best_lo = mn; k_near = k; }
+        if (mx < best_hi) { best_hi = mx; k_far = k; }
+    }
+    float dc[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f};
+    const bool hit = tf > 0.f;
+    if (hit && tn > 0.f) { dc[k_near] += -g_near / d[k_near]; dr[k_near] += -g_near * tn / d[k_near]; }
+    if (hit) { dc[k_far] += -g_far / d[k_far]; dr[k_far] += -g_far * tf / d[k_far]; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { d_center[3 * r + k] = dc[k]; d_ray[3 * r + k] = dr[k]; }
+}
+
 // ---------------------------------------------------------------- warp scan helpers
 LS_DEV float ls_warp_incl_scan(float v, int lane) {
 #pragma unroll

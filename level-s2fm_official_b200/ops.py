@@ -472,24 +472,13 @@ class Composite(torch.autograd.Function):
         return d_ray, d_t, d_sdf, d_rgbs, d_nrm, None if sink is not None else d_beta.view_as(beta_param), None, None
 
 
-def _aabb_vjp(c, r, hits, g_near, g_far, bmin, bmax):
-    """VJP of the slab test the reference's RayAABBIntersector lacks (utils/custom_functions.py:10-31; SURVEY 8a defect iii):
-    on the slab axis k that decides t_near / t_far,  dt/do_k = -1/d_k,  dt/dd_k = -t/d_k;  zero where t_near was clamped to 0 or
-    the ray misses the box.  c, r [M,3]; hits [M,2]; g_near, g_far [M] -> (d_c, d_r)."""
-    lo_p = torch.tensor(bmin, device=c.device, dtype=c.dtype)
-    hi_p = torch.tensor(bmax, device=c.device, dtype=c.dtype)
-    inv = 1.0 / r
-    t_lo, t_hi = (lo_p - c) * inv, (hi_p - c) * inv
-    k_near = torch.minimum(t_lo, t_hi).argmax(dim=-1, keepdim=True)
-    k_far = torch.maximum(t_lo, t_hi).argmin(dim=-1, keepdim=True)
-    hit = hits[:, 1] > 0
-    g_near = torch.where(hit & (hits[:, 0] > 0), g_near, torch.zeros_like(g_near))
-    g_far = torch.where(hit, g_far, torch.zeros_like(g_far))
-    d_c, d_r = torch.zeros_like(c), torch.zeros_like(r)
-    for k, g, tv in ((k_near, g_near, hits[:, 0]), (k_far, g_far, hits[:, 1])):
-        inv_k = inv.gather(-1, k)[:, 0]
-        d_c.scatter_add_(-1, k, (-g * inv_k)[:, None])
-        d_r.scatter_add_(-1, k, (-g * tv * inv_k)[:, None])
+def _aabb_vjp(c, r, hits, g, n_samples, bmin, bmax):
+    """VJP of the slab test the reference's RayAABBIntersector lacks (utils/custom_functions.py:10-31; SURVEY 8a defect iii), one
+    launch (ls2fm_ray_aabb_backward): g [R, n_samples] on the uniform depths, or [R,2] on (t_near, t_far) when n_samples == 0."""
+    lib = _C.get()
+    d_c, d_r = torch.empty_like(c), torch.empty_like(r)
+    _call(lib, "ray_aabb_backward", lib.dll.ls2fm_ray_aabb_backward, lib.ptr(c), lib.ptr(r), c.shape[0], int(n_samples), _C.f3(bmin), _C.f3(bmax),
+          lib.ptr(hits), lib.ptr(g.contiguous().float()), lib.ptr(d_c), lib.ptr(d_r), lib.stream())
     return d_c, d_r
 
 
@@ -511,7 +500,7 @@ class RayAABB(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_hits):
         o, d, hits = ctx.saved_tensors
-        d_o, d_d = _aabb_vjp(o, d, hits, g_hits[:, 0], g_hits[:, 1], *ctx.misc)
+        d_o, d_d = _aabb_vjp(o, d, hits, g_hits, 0, *ctx.misc)
         return d_o, d_d, None, None
 
 
@@ -534,10 +523,7 @@ class UniformDepths(torch.autograd.Function):
     def backward(ctx, g_t):
         c, r, hits = ctx.saved_tensors
         n, bmin, bmax = ctx.misc
-        frac = (torch.arange(n, device=g_t.device, dtype=g_t.dtype) + 0.5) / n
-        g_far = (g_t * frac).sum(-1)
-        g_near = g_t.sum(-1) - g_far
-        d_c, d_r = _aabb_vjp(c, r, hits, g_near, g_far, bmin, bmax)
+        d_c, d_r = _aabb_vjp(c, r, hits, g_t, n, bmin, bmax)
         return d_c, d_r, None, None, None
 
 

@@ -136,9 +136,9 @@ def test_reference_ba_iteration_on_dropin_models(dual):
     lr, retr, gx_r, gse_r, gcam_r = _one_ba_iteration(pl, opt, cams, intr, xyzs, rgbs_gt, kp_fwd, r_sdf, r_rad, r_ren)
     lo, reto, gx_o, gse_o, gcam_o = _one_ba_iteration(pl, opt, cams, intr, xyzs, rgbs_gt, kp_fwd, o_sdf, o_rad, o_ren)
 
-    same_finish = abs(float(lo["DC_Loss"]) - float(lr["DC_Loss"])) <= 5e-2 * max(abs(float(lr["DC_Loss"])), 1e-6)
+    same_finish = abs(float(lo["DC_Loss"].detach()) - float(lr["DC_Loss"].detach())) <= 5e-2 * max(abs(float(lr["DC_Loss"].detach())), 1e-6)
     for k in lr:                      # every loss term the stage computes + the weighted sum
-        a, b = float(lo[k]), float(lr[k])
+        a, b = float(torch.as_tensor(lo[k]).detach()), float(torch.as_tensor(lr[k]).detach())
         # DC_Loss = mean 0.5 (d_traced - d_rendered)^2 with the two depths ~2 and their difference ~0.05.  The traced depth is a sum
         # of steps each of which is zeroed when |sdf| <= sdf_threshold = 1e-3 (models/SDF.py:153-157): a discontinuity of size 1e-3
         # in d_traced, i.e. up to 1e-3 / 0.05 = 2 % of a ray's difference and twice that of its square.  All other terms: 1e-4.
@@ -149,7 +149,7 @@ def test_reference_ba_iteration_on_dropin_models(dual):
     assert torch.equal(reto.mask_bg, retr.mask_bg)
     for k in ("rgb", "depth_mlp", "normal_mlp", "sdfs_volume", "normals"):
         assert common.rel_err(reto[k].detach(), retr[k].detach()) < 1e-4, k
-    assert abs(float(reto.PSNR) - float(retr.PSNR)) < 1e-3
+    assert abs(float(reto.PSNR.detach()) - float(retr.PSNR.detach())) < 1e-3
     assert common.cosine(gx_o, gx_r) > 1 - 1e-6 and common.rel_err(gx_o, gx_r) < 2e-3                  # tracked 3-D points
     assert common.cosine(gse_o, gse_r) > 1 - 1e-6 and common.rel_err(gse_o, gse_r) < 2e-3              # poses (reprojection term)
     n = 0

@@ -47,3 +47,11 @@ for req in (False, True):
     d = {k: sum(v) / 5 for k, v in ops.KLOG.durations_ms().items()}
     print(f"rays require grad = {req}: {a.elapsed_time(b) / 5:.3f} ms / iteration; field_backward {d.get('field_backward', 0):.3f} ms, "
           f"field_forward {d.get('field_forward', 0):.3f} ms")
+
+if os.environ.get("LS2FM_PROFILE"):
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(3):
+            run(True)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
