@@ -461,7 +461,7 @@ def main():
     ap.add_argument("--e2e-sync-readback", action="store_true", help="diagnostic: read the loss back with .item() every step")
     ap.add_argument("--graph", choices=["on", "off"], default="on",
                     help="replay the iteration's compute (sampler .. backward) as one CUDA graph (levels2fm_b200.graph.GraphedStep); "
-                         "workloads with a host read-back (c4: sphere_tracing) always run eagerly")
+                         "c4 then runs sphere_tracing in its synchronisation-free form (SDF.st_sync_free)")
     args = ap.parse_args()
     if args.workload in FORWARD_ONLY:
         if args.impl == "reference":
@@ -550,7 +550,9 @@ def main():
         loss.backward()
         return loss.detach(), out["sdfs_volume"].detach()
 
-    use_graph = args.graph == "on" and not wl.get("trace")
+    use_graph = args.graph == "on"
+    if wl.get("trace") and use_graph:
+        sdf.st_sync_free = True      # sphere_tracing without its host read-back of the iteration count (same d_pred / finish_mask)
     graphed = None
     launches_per_step = None
     if use_graph:

@@ -32,6 +32,8 @@ class SDF(nn.Module):
         self.sdf_threshold = float(v.sdf_threshold)
         self.iters_max = int(v.iters_max_st)
         self.scale_mlp = opt.SDF.NN_Init.scale_mlp
+        # sphere_tracing without its one host read-back (see the method): off by default = the reference's exact output shapes
+        self.st_sync_free = False
         self.define_network(opt)
 
     def define_network(self, opt):
@@ -164,11 +166,30 @@ class SDF(nn.Module):
         track, cnt, t_near, t_far, acc_hist = ops.sphere_trace_raw(
             _C.get(), self.field_spec(), self.table().detach(), self.SDF_MLP.theta().detach().contiguous(), o, d,
             self.sdf_threshold, self.iters_max)
-        done = (cnt == 0).nonzero()
-        n_it = int(done[0, 0]) if done.numel() else self.iters_max          # iterations the reference's loop runs
-        acc_e = acc_hist[n_it]
-        pts_tracks = track[:, :max(n_it, 1)]                                # [M,K,3]; K = 0 keeps the start point
-        sdf_tracks = self.infer_sdf(pts_tracks)                          # [M,K,1], with grad
+        if self.st_sync_free:
+            # K (the iteration count of the reference's loop) stays on the device: all iters_max track rows are evaluated, rows >= K
+            # are masked out of the sum and replaced by the last valid point (so the field sees finite inputs).  d_pred, sdf_last,
+            # finish_mask and their gradients are those of the synchronous form; only sampled_pts differs when K < iters_max (it
+            # then carries iters_max instead of K rows per ray, the extra ones repeating the last point).  No host synchronisation:
+            # the whole iteration becomes capturable in a CUDA graph (graph.GraphedStep).
+            is_zero = cnt[:self.iters_max] == 0
+            K_t = torch.where(is_zero.any(), is_zero.float().argmax(), torch.full((), self.iters_max, device=cnt.device)).long()
+            Kc = K_t.clamp_min(1)
+            mask = (torch.arange(self.iters_max, device=cnt.device) < Kc)
+            last = track.gather(1, (Kc - 1).view(1, 1, 1).expand(track.shape[0], 1, 3))
+            pts_tracks = torch.where(mask[None, :, None], track, last)
+            sdf_tracks = self.infer_sdf(pts_tracks)                                     # [M, iters_max, 1], with grad
+            d_sum = (sdf_tracks * mask[None, :, None]).sum(dim=-2)
+            sdf_last = sdf_tracks.gather(1, (Kc - 1).view(1, 1, 1).expand(track.shape[0], 1, 1))[:, 0, :]
+            acc_e = acc_hist.index_select(0, K_t.view(1))[0]
+        else:
+            done = (cnt == 0).nonzero()
+            n_it = int(done[0, 0]) if done.numel() else self.iters_max          # iterations the reference's loop runs
+            acc_e = acc_hist[n_it]
+            pts_tracks = track[:, :max(n_it, 1)]                                # [M,K,3]; K = 0 keeps the start point
+            sdf_tracks = self.infer_sdf(pts_tracks)                          # [M,K,1], with grad
+            d_sum = sdf_tracks.sum(dim=-2)
+            sdf_last = sdf_tracks[:, -1, :]
         if torch.is_grad_enabled() and (ray0.requires_grad or ray_direction.requires_grad):
             # d_pred = sum sdf(track points, constants) + t_near, clamped to t_far: the rays enter through the slab test only
             # (models/SDF.py:120-123,204-205).  The reference's RayAABBIntersector has no backward; ours has (SURVEY 8a defect
@@ -179,10 +200,10 @@ class SDF(nn.Module):
             hits = ops.RayAABB.apply(ray0.reshape(-1, 3), ray_direction.reshape(-1, 3), [float(x) for x in self.opt.data.bound_min],
                                      [float(x) for x in self.opt.data.bound_max])
             t_near, t_far = hits[:, 0], hits[:, 1]
-        d_pred = sdf_tracks.sum(dim=-2).view(*ray0.shape[:-1]) + t_near.view(*ray0.shape[:-1])
+        d_pred = d_sum.view(*ray0.shape[:-1]) + t_near.view(*ray0.shape[:-1])
         d_pred = torch.minimum(d_pred, t_far.view(*d_pred.shape))
         thr2 = float(self.opt.data.bound_max[0] - self.opt.data.bound_min[0]) / 10 / self.opt.Res
-        finish_mask = sdf_tracks[:, -1, :].abs() < thr2
+        finish_mask = sdf_last.abs() < thr2
         # random points for the eikonal term (models/SDF.py:216-224)
         tf_v, tn_v = t_far.view(*d_pred.shape), t_near.view(*d_pred.shape)
         factor_rand = torch.rand_like(d_pred)
@@ -191,4 +212,4 @@ class SDF(nn.Module):
         sampled_pts = ray0 + d_sample[..., None] * ray_direction          # (callers detach it, e.g. pipelines/Camera.py:243)
         pick = torch.randperm(pts_tracks.shape[0], device=pts_tracks.device)[:4096]
         sampled_pts = torch.cat([pts_tracks[pick].view(1, -1, 3), sampled_pts.view(1, -1, 3)], dim=1)
-        return d_pred, sdf_tracks[:, -1, 0], sampled_pts, finish_mask
+        return d_pred, sdf_last[:, 0], sampled_pts, finish_mask

@@ -386,3 +386,38 @@ def grid_encode_double_backward_case(device, m=200, n_levels=16):
     for name, a, b in zip(("d/d table", "d/d u", "d/d w", "first-order d_u"), res["ours"], res["ref"]):
         assert common.cosine(a, b) > 1 - 1e-6, (name, common.cosine(a, b))
         assert common.rel_err(a, b) < 2e-3, (name, common.rel_err(a, b))
+
+
+def sphere_trace_sync_free_case(device):
+    """SDF.st_sync_free: the iteration count stays on the device (no host read-back, graph-capturable); d_pred, sdf_last,
+    finish_mask and the parameter gradients are those of the default form -- with K == iters_max (the fixture) and with an early
+    global stop (clean sphere, K < iters_max)."""
+    gold = load("st_dtu.npz")
+    for early in (False, True):
+        opt = common.make_opt("DTU", device, 16, **({"SDF.VolSDF.iters_max_st": 40} if early else {}))
+        sdf, _, _ = common.build_models(opt)
+        if early:
+            sd, _ = port.random_state(port.SceneCfg(n_levels=16, iters_max_st=40), seed=4, table_std=1e-4, generic_weights=False)
+            c, r = common.make_rays(1, 32, 1.0, seed=2)
+            r = r * 0 + torch.tensor([0.0, 0.0, 1.0])
+            c = c * 0.05 + torch.tensor([0.0, 0.0, -2.5])
+        else:
+            sd, c, r = st_state(), gold["center"], gold["ray"]
+        sdf.load_state_dict(sd)
+        res = {}
+        for mode in (False, True):
+            sdf.st_sync_free = mode
+            for p in sdf.parameters():
+                p.grad = None
+            d_pred, sdf_last, pts, finish = sdf.sphere_tracing(c.to(device), r.to(device), sdf)
+            d_pred.sum().backward()
+            res[mode] = (d_pred.detach().cpu(), sdf_last.detach().cpu(), finish.cpu(), pts.shape,
+                         {k: p.grad.cpu().clone() for k, p in sdf.named_parameters() if p.grad is not None})
+        a, b = res[True], res[False]
+        assert torch.allclose(a[0], b[0], atol=1e-6, rtol=1e-6) and torch.allclose(a[1], b[1], atol=1e-7) and torch.equal(a[2], b[2])
+        assert (a[3][1] > b[3][1]) if early else (a[3] == b[3])           # sampled_pts: padded to iters_max rows only on an early stop
+        for k in b[4]:
+            if float(b[4][k].abs().max()) == 0.0:
+                assert float(a[4][k].abs().max()) == 0.0, k
+                continue
+            assert common.cosine(a[4][k], b[4][k]) > 1 - 1e-9, k

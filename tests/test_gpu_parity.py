@@ -507,3 +507,7 @@ def test_standalone_grid_encoding_is_double_differentiable():
 def test_position_gradients_on_the_tensor_core_route(dataset, dual, n_rays, n_samples):
     from . import input_grad_checks as ig
     ig.tensor_core_route_matches_simt_route(DEV, n_rays=n_rays, n_samples=n_samples, dataset=dataset, dual=dual)
+
+
+def test_sphere_tracing_sync_free_form_equals_default():
+    gc.sphere_trace_sync_free_case(DEV)

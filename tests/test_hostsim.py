@@ -366,3 +366,7 @@ def test_standalone_grid_encoding_is_double_differentiable():
 def test_position_gradients_on_the_tensor_core_route(dataset, dual):
     from . import input_grad_checks as ig
     ig.tensor_core_route_matches_simt_route("cpu", n_rays=9, n_samples=15, dataset=dataset, dual=dual)
+
+
+def test_sphere_tracing_sync_free_form_equals_default():
+    gc.sphere_trace_sync_free_case("cpu")
