@@ -604,7 +604,7 @@ int ls2fm_sample_error_bounded(const ls2fm_field_t* sdf_field, const float* beta
         p.ray_index = a.ray_index + (size_t)it * n_rays;
         p.n_active = a.cnt + it;
         if (ls2fm_field_forward(sdf_field, &p, nullptr, nullptr, a.S, nullptr, nullptr, stream)) return 1;
-        LS_LAUNCH(ls_sampler_round_kernel, grid, wpb * 32, smem_round, stream, a, it);
+        LS_LAUNCH(ls_sampler_round_kernel, grid, wpb * 32, wpb * 5 * a.N * (it + 1) * (int)sizeof(float), stream, a, it);
         if (ls_check_launch("sampler_round")) return 1;
     }
     LS_LAUNCH(ls_sampler_finalize_kernel, grid, wpb * 32, smem_final, stream, a, t_out, beta_plus, iters);

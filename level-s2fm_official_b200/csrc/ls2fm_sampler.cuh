@@ -137,16 +137,16 @@ __global__ void ls_sampler_init_kernel(const LsSamplerArgs a) {
 }
 
 // ---------------------------------------------------------------- one round
-// dynamic smem per warp: 5 * Mmax floats (d, s, scratch b, merge buffers d2, s2)
+// dynamic smem per warp: 5 * M floats, M = N (it + 1) (d, s, scratch b, merge buffers d2, s2)
 __global__ void ls_sampler_round_kernel(const LsSamplerArgs a, int it) {
     LS_DYN_SMEM(smem);
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = blockIdx.x * wpb + warp;
     if (slot >= a.cnt[it]) return;
     const int r = a.ray_index[(int64_t)it * a.n_rays + slot];
-    float* d = smem + warp * 5 * a.Mmax;
-    float* s = d + a.Mmax; float* b = s + a.Mmax; float* d2 = b + a.Mmax; float* s2 = d2 + a.Mmax;
     const int N = a.N, Mold = N * it, M = Mold + N;
+    float* d = smem + warp * 5 * M;     // (arrays sized for THIS round's M, not Mmax: the early rounds -- the ones with many rays -- get 3-6x the warps per SM)
+    float* s = d + M; float* b = s + M; float* d2 = b + M; float* s2 = d2 + M;
     float* Dg = a.D + (int64_t)r * a.Mmax;
     float* Sg = a.S + (int64_t)r * a.Mmax;
     // ---- load + rank-merge (old sorted prefix, new sorted tail)

@@ -89,3 +89,36 @@ def image_case(device, H=12, W=16, dataset="DTU", dual=False, slice_rays=50, eb=
             # golden_checks.check_c2 -- typical ray at 1e-4, nearly all at 1e-3
             e = (a - b).abs().amax(dim=-1) / b.abs().max()
             assert e.median().item() < 1e-4 and (e < 1e-3).float().mean().item() > 0.8, (key, e.median().item(), (e < 1e-3).float().mean().item())
+
+
+def values_only_kernel_case(device, n, layers, n_levels=16, ray_mode=False):
+    """The two-tiles-in-flight values-only kernel (sampler rounds, infer_sdf, the SDF volume): several tile pairs per CTA, ragged
+    tails, every MLP depth (1, 2, 3 hidden layers), explicit points and ray samples -- against the exact fp32-SIMT kernel of the
+    same library (2e-6) and the oracle (1e-4)."""
+    from levels2fm_b200 import _C, ops
+    lib = _C.get()
+    opt = common.make_opt("DTU", device, n_levels, layers, 16)
+    cfg = common.cfg_of(opt, n_levels)
+    sdf_sd, _ = port.random_state(cfg, seed=6, table_std=0.2)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    spec, table = sdf.field_spec(), sdf.table().detach()
+    theta = sdf.SDF_MLP.theta().detach().contiguous()
+    g = torch.Generator().manual_seed(n)
+    if ray_mode:
+        n_per_ray = 7
+        n_rays = (n + n_per_ray - 1) // n_per_ray
+        center = (torch.rand(n_rays, 3, generator=g) * 0.6 - 0.3).to(device).contiguous()
+        ray = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g), dim=-1).to(device).contiguous()
+        t = (torch.rand(n_rays, n_per_ray, generator=g) * 0.6).to(device).contiguous()
+        pts = ops._points(lib, None, center, ray, t)
+        x = (center[:, None] + ray[:, None] * t[..., None]).reshape(-1, 3)
+    else:
+        x = (torch.rand(n, 3, generator=g) * 1.6 - 0.8).to(device).contiguous()
+        pts = ops._points(lib, x, None, None, None)
+    image = ops.field_prepare_raw(lib, spec, table, theta, None)
+    y, s, _, _ = ops.field_forward_raw(lib, spec, table, theta, pts, None, want_y=True, image=image)
+    y_ref, s_ref, _, _ = ops.field_forward_raw(lib, spec, table, theta, pts, None, want_y=True, simt=True)
+    assert common.rel_err(y, y_ref) < 2e-6 and common.rel_err(s, s_ref) < 2e-6
+    o_sdf, _ = port.infer_sdf(x.cpu(), sdf_sd, cfg, "ret_all")
+    assert common.rel_err(s.cpu(), o_sdf.reshape(-1)) < 1e-4

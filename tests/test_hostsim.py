@@ -370,3 +370,10 @@ def test_position_gradients_on_the_tensor_core_route(dataset, dual):
 
 def test_sphere_tracing_sync_free_form_equals_default():
     gc.sphere_trace_sync_free_case("cpu")
+
+
+@pytest.mark.parametrize("n,layers,ray_mode", [(1500, (None, 64, 64, 64, 16), False), (1100, (None, 64, 64, 16), True), (900, (None, 64, 16), False),
+                                               (257, (None, 64, 64, 64, 16), True)])
+def test_values_only_kernel_many_pairs_all_depths(n, layers, ray_mode):
+    from . import inference_checks as ic
+    ic.values_only_kernel_case("cpu", n, layers, ray_mode=ray_mode)
