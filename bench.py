@@ -674,10 +674,19 @@ def main():
     tr_path = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
     if os.path.exists(tr_path) and args.workload == "c2":
         traffic = json.load(open(tr_path)).get(dom)          # dram__bytes_read + dram__bytes_write per launch (ncu --set full)
+    # what the load/store path allows for this kernel's scattered 8-byte accesses (measured with stand-alone gather / scatter kernels on
+    # the same samples, profiles/l1tex_floor_r2.json): the ceiling the HBM-based `frac` can reach for this access pattern
+    attainable = None
+    fl_path = os.path.join(ROOT, "profiles", "l1tex_floor_r2.json")
+    if os.path.exists(fl_path) and dom in ("field_backward", "field_forward"):
+        fl = json.load(open(fl_path))
+        floor_ms = S * (fl["gather_ns_per_sample"] + (fl["scatter_ns_per_sample"] if dom == "field_backward" else 0.0)) * 1e-6
+        attainable = {"floor_ms": floor_ms, "frac_at_floor": alg / (floor_ms * 1e-3) / 1e9 / peak, "launch_ms_over_floor": big_ms / floor_ms,
+                      "what": "L1TEX-bound gather" + (" + scatter" if dom == "field_backward" else "") + " of this launch's samples, nothing else (profiles/l1tex_floor_r2.json)"}
     # the sampler's up-sampling rounds that actually ran (rays still active), for the whole-step algorithmic bytes
     bpr = bytes_per_ray(wl, int(n_samples), n_trace=(3 * 10 if wl.get("trace") else 0))
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback", "attainable": attainable,
                 "algorithmic_bytes_per_launch": alg, "launch_ms": big_ms, "launch_samples": S,
                 "launches_of_this_kernel_per_step": len(per_name[dom]) // n_prof,
                 "kernel_ms_per_step": per_step_kernel_ms,
