@@ -10,6 +10,7 @@
 #include "ls2fm_field.cuh"
 #include "ls2fm_field_tc.cuh"
 #include "ls2fm_field_bwtc.cuh"
+#include "ls2fm_field_bwfeat.cuh"
 #include "ls2fm_field_ws.cuh"
 #include "ls2fm_render.cuh"
 #include "ls2fm_sampler.cuh"
@@ -436,8 +437,8 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
     // ---- tensor-core kernel: needs the operand image (weights stream from it), the 2-channel form (normals carry gradient),
     //      chunk-aligned level groups and matrices that fit a ring slot; everything else runs the fp32-SIMT kernel below
     //      Launches below LS_BT_MIN_SAMPLES stay on the SIMT kernel: a few tiles do not amortise the tensor-core kernel's set-up.
-    // (a launch without a gradient on the normals -- RadF.Geo_enc under dual_field: g_y only -- runs the same kernel with a zero
-    //  tangent channel: every second-order term vanishes identically, and it is still faster than the fp32-SIMT first-order kernel)
+    // (a launch without a gradient on the normals -- RadF.Geo_enc under dual_field: g_y only -- runs the single-channel variant
+    //  ls_field_backward_feat_tc_kernel: 128 samples per tile instead of 64 samples x 2 channels)
     //  position gradients: the tensor-core kernel parks the encoding adjoints in ig.workspace and ls_field_posgrad_kernel finishes)
     const bool tc_ok = field->tc_image && (field->n_levels & 3) == 0 && (!want_dx || a.ig.workspace) && (tan || g_y || g_sdf);
     if (!want_dx) a.ig.workspace = nullptr;
@@ -451,14 +452,16 @@ static int ls_field_backward_impl(const ls2fm_field_t* field, const ls2fm_points
         for (int l = 0; l < KL - 1; ++l) fits = fits && img.n_out_pad[l] * img.k_in_pad[l] <= LS_BT_SLOT && img.n_in_pad[l] * LS_H <= LS_BT_SLOT;
         if (fits) {
             a.net = ls_plan_net(*field, with_rad ? rad->in_dim : 0, 1, false);        // theta offsets
-            const int64_t n_tiles = (pts->n + LS_BT_TILE - 1) / LS_BT_TILE;
+            // no gradient on the normals (RadF.Geo_enc under dual_field: g_y only): the single-channel kernel, 128 samples per tile
+            const int64_t n_tiles = tan ? (pts->n + LS_BT_TILE - 1) / LS_BT_TILE : (pts->n + LS_BF_TILE - 1) / LS_BF_TILE;
             const int64_t grid = n_tiles < ls_sm_count() ? n_tiles : ls_sm_count();
-#define LS_BT_LAUNCH(KV)                                                                                   \
+#define LS_BT_LAUNCH(KERNEL, KV)                                                                           \
             do {                                                                                           \
-                if (ls_opt_in_smem(ls_field_backward_tc_kernel<KV>, smem)) return 1;                       \
-                LS_LAUNCH((ls_field_backward_tc_kernel<KV>), (unsigned)grid, LS_BT_THREADS, smem, stream, a, img, net); \
+                if (ls_opt_in_smem(KERNEL<KV>, smem)) return 1;                                            \
+                LS_LAUNCH((KERNEL<KV>), (unsigned)grid, LS_BT_THREADS, smem, stream, a, img, net);         \
             } while (0)
-            if (KL == 2) LS_BT_LAUNCH(2); else if (KL == 3) LS_BT_LAUNCH(3); else LS_BT_LAUNCH(4);
+            if (tan) { if (KL == 2) LS_BT_LAUNCH(ls_field_backward_tc_kernel, 2); else if (KL == 3) LS_BT_LAUNCH(ls_field_backward_tc_kernel, 3); else LS_BT_LAUNCH(ls_field_backward_tc_kernel, 4); }
+            else { if (KL == 2) LS_BT_LAUNCH(ls_field_backward_feat_tc_kernel, 2); else if (KL == 3) LS_BT_LAUNCH(ls_field_backward_feat_tc_kernel, 3); else LS_BT_LAUNCH(ls_field_backward_feat_tc_kernel, 4); }
 #undef LS_BT_LAUNCH
             if (ls_check_launch("field_backward(tc)")) return 1;
             if (want_dx) {

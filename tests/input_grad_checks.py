@@ -273,3 +273,47 @@ def tensor_core_route_matches_simt_route(device, n_rays=70, n_samples=33, datase
         assert float(b.abs().max()) > 0, name
         assert common.cosine(a, b) > 1 - 1e-7, (name, common.cosine(a, b))
         assert common.rel_err(a, b) < 2e-4, (name, common.rel_err(a, b))
+
+
+def feature_only_tensor_core_backward(device, n, layers, ray_mode=False, want_dx=True, seed=0):
+    """ls_field_backward_feat_tc_kernel (no gradient on the normals: RadF.Geo_enc under dual_field, models/RadF.py:53-63; 128-sample
+    tiles, one channel) forced through ls2fm_field_backward_tc against the exact fp32-SIMT kernel: table / weight / bias gradients
+    and the position gradients (d_xyz, or d_center / d_ray / d_t in ray mode), on tile-edge and multi-tile sizes."""
+    from levels2fm_b200 import _C, ops
+    lib = _C.get()
+    opt = common.make_opt("DTU", device, 16, layers, 16)
+    cfg = common.cfg_of(opt, 16)
+    sdf_sd, _ = port.random_state(cfg, seed=4 + seed, table_std=0.2)
+    sdf, _, _ = common.build_models(opt)
+    sdf.load_state_dict(sdf_sd)
+    spec, table = sdf.field_spec(), sdf.table().detach()
+    theta = sdf.SDF_MLP.theta().detach().contiguous()
+    g = torch.Generator().manual_seed(n + seed)
+    if ray_mode:
+        npr = 5
+        n_rays = (n + npr - 1) // npr
+        n = n_rays * npr
+        center = (torch.rand(n_rays, 3, generator=g) * 0.6 - 0.3).to(device).contiguous()
+        ray = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g), dim=-1).to(device).contiguous()
+        tt = (torch.rand(n_rays, npr, generator=g) * 0.6).to(device).contiguous()
+        pts = ops._points(lib, None, center, ray, tt)
+    else:
+        x = (torch.rand(n, 3, generator=g) * 1.6 - 0.8).to(device).contiguous()
+        pts = ops._points(lib, x, None, None, None)
+    g_y = torch.randn(n, spec.dout, generator=g).to(device).contiguous()
+    g_sdf = torch.randn(n, generator=g).to(device).contiguous()
+    image = ops.field_prepare_raw(lib, spec, table, theta, None)
+    out = {}
+    for mode in ("tc", "simt"):
+        d_table, d_theta = torch.zeros_like(table), torch.zeros_like(theta)
+        kw = {}
+        if want_dx and ray_mode:
+            kw = dict(d_center=torch.zeros(n_rays, 3, device=device), d_ray=torch.zeros(n_rays, 3, device=device), d_t=torch.zeros(n_rays, npr, device=device))
+        elif want_dx:
+            kw = dict(d_xyz=torch.zeros(n, 3, device=device))
+        ops.field_backward_raw(lib, spec, table, theta, pts, None, g_y, g_sdf, None, None, None, None, d_table, d_theta, image=image, mode=mode, **kw)
+        out[mode] = dict(d_table=d_table, d_theta=d_theta, **kw)
+    for k in out["tc"]:
+        a, b = out["tc"][k], out["simt"][k]
+        assert float(b.abs().max()) > 0, k
+        assert common.rel_err(a, b) < 5e-5, (k, common.rel_err(a, b))

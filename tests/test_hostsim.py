@@ -377,3 +377,10 @@ def test_sphere_tracing_sync_free_form_equals_default():
 def test_values_only_kernel_many_pairs_all_depths(n, layers, ray_mode):
     from . import inference_checks as ic
     ic.values_only_kernel_case("cpu", n, layers, ray_mode=ray_mode)
+
+
+@pytest.mark.parametrize("n,layers,ray_mode", [(1, (None, 64, 16), False), (127, (None, 64, 16), True), (128, (None, 64, 64, 16), False), (129, (None, 64, 64, 64, 16), False),
+                                               (700, (None, 64, 16), False), (520, (None, 64, 64, 64, 16), True)])
+def test_feature_only_tensor_core_backward(n, layers, ray_mode):
+    from . import input_grad_checks as ig
+    ig.feature_only_tensor_core_backward("cpu", n, layers, ray_mode=ray_mode)
