@@ -45,7 +45,10 @@ LS_DEV float ls_linspace01(int i, int n) {
 
 // Renderer.error_bound over the ray's M sorted samples; writes bound[0..M-2] (when out != nullptr), returns the max.
 // clampit: torch.clamp(bounds, 0, 1e5) of Renderer.py:300.
-LS_DEV float ls_error_bound(const float* d, const float* s, int M, float alpha, float beta, float* out, bool clampit, int lane) {
+// stop_above >= 0: the caller only compares the maximum with this threshold -- return +inf as soon as one chunk exceeds it (same decision,
+// the remaining chunks are not evaluated).
+LS_DEV float ls_error_bound(const float* d, const float* s, int M, float alpha, float beta, float* out, bool clampit, int lane,
+                            float stop_above = -1.f) {
     float carryR = 0.f, carryE = 0.f, mx = -INFINITY;
     const float k = alpha / (4.f * beta);
     for (int base = 0; base < M - 1; base += 32) {
@@ -69,6 +72,7 @@ LS_DEV float ls_error_bound(const float* d, const float* s, int M, float alpha, 
             mx = fmaxf(mx, b);
             if (out) out[i] = b;
         }
+        if (stop_above >= 0.f && __any_sync(0xffffffffu, on && b > stop_above)) return INFINITY;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -158,18 +162,22 @@ __global__ void ls_sampler_round_kernel(const LsSamplerArgs a, int it) {
         // stable merge that does not rely on the new tail being sorted (it is, up to an ulp of rounding in the
         // inverse-CDF interpolation; the reference simply torch.sort()s the concatenation)
         const float* nw = d2 + Mold;
+        bool tail_sorted = true;                                // (it is, up to that ulp: then both ranks are binary searches)
+        for (int j = lane; j < N - 1; j += 32) tail_sorted = tail_sorted && nw[j] <= nw[j + 1];
+        tail_sorted = __all_sync(0xffffffffu, tail_sorted);
         for (int i = lane; i < Mold; i += 32) {                 // old element: i + #{new < old_i}
             const float v = d2[i];
             int c = 0;
-            for (int j = 0; j < N; ++j) c += nw[j] < v ? 1 : 0;
+            if (tail_sorted) c = ls_lower_bound(nw, N, v);
+            else for (int j = 0; j < N; ++j) c += nw[j] < v ? 1 : 0;
             d[i + c] = v; s[i + c] = s2[i];
         }
         for (int j = lane; j < N; j += 32) {                    // new element: #{old <= new_j} + rank inside the tail
             const float v = nw[j];
             int lo = 0, hi = Mold;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (d2[mid] <= v) lo = mid + 1; else hi = mid; }
-            int c = 0;
-            for (int k = 0; k < N; ++k) c += (nw[k] < v || (nw[k] == v && k < j)) ? 1 : 0;
+            int c = j;                                          // sorted tail: everything before j is <= v, nothing after j is < v
+            if (!tail_sorted) { c = 0; for (int k = 0; k < N; ++k) c += (nw[k] < v || (nw[k] == v && k < j)) ? 1 : 0; }
             d[lo + c] = v; s[lo + c] = s2[Mold + j];
         }
     }
@@ -178,7 +186,7 @@ __global__ void ls_sampler_round_kernel(const LsSamplerArgs a, int it) {
     // ---- converged with the network's beta?
     const float beta_net = expf(__ldg(a.beta_param) * a.beta_speed);
     const float alpha_net = 1.f / beta_net;
-    const float mx = ls_error_bound(d, s, M, alpha_net, beta_net, nullptr, false, lane);
+    const float mx = ls_error_bound(d, s, M, alpha_net, beta_net, nullptr, false, lane, a.eps);
     if (!(mx > a.eps)) {
         ls_opacity_samples(d, s, M, alpha_net, beta_net, b, a.Nf, a.fine + (int64_t)r * a.Nf, lane);
         if (lane == 0) { a.state[r] = 1; a.iters[r] = (float)it; a.beta_plus[r] = beta_net; }
@@ -190,7 +198,7 @@ __global__ void ls_sampler_round_kernel(const LsSamplerArgs a, int it) {
         float bl = beta_net, br = bp;
         for (int k = 0; k < a.max_bisect; ++k) {
             const float bm = 0.5f * (bl + br);
-            const float m2 = ls_error_bound(d, s, M, 1.f / bm, bm, nullptr, false, lane);
+            const float m2 = ls_error_bound(d, s, M, 1.f / bm, bm, nullptr, false, lane, a.eps);
             if (m2 <= a.eps) br = bm; else bl = bm;
         }
         bp = br;
@@ -251,10 +259,24 @@ __global__ void ls_sampler_finalize_kernel(const LsSamplerArgs a, float* __restr
     // rank of every element of the union by counting (ties broken by position): equal to a stable sort, and safe
     // for rays that miss the box (all coarse depths equal -1) or whose fine samples coincide
     const int T = a.N + a.Nf;
+    // both halves sorted (the usual case): the rank is the position inside the own half plus a binary search in the other one
+    // (coarse before fine among equals, like the stable sort of the concatenation)
+    bool both_sorted = true;
+    for (int i = lane; i < T - 1; i += 32) both_sorted = both_sorted && (i == a.N - 1 || co[i] <= co[i + 1]);
+    both_sorted = __all_sync(0xffffffffu, both_sorted);
     for (int i = lane; i < T; i += 32) {
         const float v = co[i];
         int c = 0;
-        for (int k = 0; k < T; ++k) c += (co[k] < v || (co[k] == v && k < i)) ? 1 : 0;
+        if (both_sorted) {
+            if (i < a.N) c = i + ls_lower_bound(fi, a.Nf, v);                      // #{fine < v}
+            else {                                                                  // #{coarse <= v}
+                int lo = 0, hi = a.N;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (co[mid] <= v) lo = mid + 1; else hi = mid; }
+                c = lo + (i - a.N);
+            }
+        } else {
+            for (int k = 0; k < T; ++k) c += (co[k] < v || (co[k] == v && k < i)) ? 1 : 0;
+        }
         out[c] = v;
     }
     if (lane == 0) {
