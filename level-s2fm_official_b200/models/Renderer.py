@@ -62,7 +62,7 @@ class Renderer:
             c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
             prepared = prepared or self._prepare(SDF_Field)
             t, beta_plus, iters = sampler.error_bounded(self, opt, c2, r2, SDF_Field, prepared)
-            return t.view(B, R, -1), beta_plus.view(B, R), iters.view(B, R)
+            return t.view(B, R, t.shape[-1]), beta_plus.view(B, R), iters.view(B, R)
         bmin, bmax = [float(x) for x in opt.data.bound_min], [float(x) for x in opt.data.bound_max]
         if torch.is_grad_enabled() and (center.requires_grad or ray.requires_grad):
             if getattr(getattr(opt, "Renderer", None), "aabb_grad", True) == False:   # noqa: E712
@@ -72,7 +72,7 @@ class Renderer:
         else:
             c2, r2 = center.detach().reshape(-1, 3).float().contiguous(), ray.detach().reshape(-1, 3).float().contiguous()
             t, _ = ops.sample_uniform_raw(_C.get(), c2, r2, int(v.sample_intvs), bmin, bmax)
-        t = t.view(B, R, -1)
+        t = t.view(B, R, t.shape[-1])       # (explicit sample count: an empty ray batch keeps its [B, 0, N] shape)
         return t, t, t
 
     # ------------------------------------------------------------------ the hot path

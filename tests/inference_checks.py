@@ -122,3 +122,26 @@ def values_only_kernel_case(device, n, layers, n_levels=16, ray_mode=False):
     assert common.rel_err(y, y_ref) < 2e-6 and common.rel_err(s, s_ref) < 2e-6
     o_sdf, _ = port.infer_sdf(x.cpu(), sdf_sd, cfg, "ret_all")
     assert common.rel_err(s.cpu(), o_sdf.reshape(-1)) < 1e-4
+
+
+def empty_batch_case(device):
+    """Zero rays / zero points through every public entry of the path: shapes follow the reference's conventions, backward runs and
+    leaves all-zero parameter gradients (no launch with an empty grid, no reshape ambiguity)."""
+    for eb in (False, True):
+        over = {"SDF.VolSDF.volsdf_sampling": True, "SDF.VolSDF.sample_intvs": 8, "SDF.VolSDF.final_sample_intvs": 8} if eb else {}
+        opt = common.make_opt("DTU", device, 16, (None, 64, 16), 16, eb, **over)      # (dual field on the second pass)
+        sdf, rad, ren = common.build_models(opt)
+        center, ray = torch.zeros(1, 0, 3, device=device), torch.zeros(1, 0, 3, device=device)
+        out = ren.forward(opt, center, ray, sdf, rad)
+        n = 16
+        assert out["rgb"].shape == (1, 0, 3) and out["normals"].shape == (1, 0, n, 3) and out["sdfs_volume"].shape == (1, 0, n, 1)
+        (out["rgb"].sum() + out["normals"].sum() + out["depth_mlp"].sum()).backward()
+        for p in list(sdf.parameters()) + list(rad.parameters()):
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+        img = ren.render_image(opt, center, ray, sdf, rad)
+        assert img["rgb"].shape == (1, 0, 3) and img["depth"].shape == (1, 0, 1)
+    x = torch.zeros(0, 3, device=device)
+    assert sdf.infer_sdf(x).shape == (0, 1)
+    assert sdf.gradient(x.clone().requires_grad_(True)).shape == (0, 3)
+    pts, _ = sdf.get_surface_pts(x)[:2]
+    assert pts.shape == (0, 3)

@@ -384,3 +384,8 @@ def test_values_only_kernel_many_pairs_all_depths(n, layers, ray_mode):
 def test_feature_only_tensor_core_backward(n, layers, ray_mode):
     from . import input_grad_checks as ig
     ig.feature_only_tensor_core_backward("cpu", n, layers, ray_mode=ray_mode)
+
+
+def test_empty_ray_and_point_batches():
+    from . import inference_checks as ic
+    ic.empty_batch_case("cpu")
