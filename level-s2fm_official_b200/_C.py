@@ -114,6 +114,7 @@ SIGNATURES = {
 
 class Lib:
     """One loaded copy of the shared library."""
+    _multi_device = None        # more than one CUDA device visible to this process (decided at the first launch)
 
     def __init__(self, path: str = LIB_PATH):
         if not os.path.exists(path):
@@ -133,6 +134,11 @@ class Lib:
     def _check_device(self, t: torch.Tensor):
         if not t.is_cuda:
             raise RuntimeError("levels2fm_b200 kernels need CUDA tensors (no CPU fallback)")
+        if self._multi_device is None:
+            self._multi_device = torch.cuda.device_count() > 1
+        if self._multi_device and t.device.index != torch.cuda.current_device():
+            # (launches go to the CURRENT device's stream: one process per GPU, or torch.cuda.device(...) around the call)
+            raise RuntimeError(f"tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}")
 
     def ptr(self, t: Optional[torch.Tensor], dtype=torch.float32):
         if t is None:
