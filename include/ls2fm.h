@@ -230,8 +230,8 @@ int ls2fm_field_backward(const ls2fm_field_t* field, const ls2fm_points_t* pts,
                          const float* saved_nrm, const float* saved_rgb,
                          float* d_table, float* d_theta, float* d_w_eff, float* d_b_eff, float* d_geo2,
                          const ls2fm_input_grads_t* in_grads, void* stream);
-/* ls2fm_field_backward dispatches: launches of >= 8192 samples (field.tc_image set, n_levels % 4 == 0, no position gradients
- * requested; launches without a gradient on the normals use a zero tangent channel) run the tcgen05 kernel -- every matrix product of the 2-channel forward / reverse pass and every weight
+/* ls2fm_field_backward dispatches: launches of >= 8192 samples (field.tc_image set, n_levels % 4 == 0; position gradients
+ * additionally need in_grads->workspace; launches without a gradient on the normals use the single-channel variant, 128 samples per tile) run the tcgen05 kernel -- every matrix product of the 2-channel forward / reverse pass and every weight
  * gradient as 3xTF32 tensor-core batches (fp32-level), weights streamed from the operand image, weight gradients accumulated in
  * TMEM, the next tile's loads and the previous tile's scatter hidden under the batches.  _simt forces the fp32-SIMT kernel
  * (cross-check and fallback), _tc forces the tensor-core kernel and fails when its preconditions do not hold. */

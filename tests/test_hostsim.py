@@ -79,7 +79,7 @@ def test_tensor_core_backward_agrees_with_simt_backward():
 
 def test_forced_tensor_core_backward_refuses_what_it_cannot_do(hostsim_lib):
     """ls2fm_field_backward_tc is strict: without the operand image (its weights stream from it) it reports an error instead of
-    silently running something else; with it, first-order launches (no gradient on the normals) run on it too."""
+    silently running something else; with it, first-order launches (no gradient on the normals) run on its single-channel variant."""
     from levels2fm_b200 import ops
     opt = common.make_opt("DTU", "cpu", 4, (None, 64, 16), 16)
     sdf, _, _ = common.build_models(opt)
@@ -101,7 +101,7 @@ def test_forced_tensor_core_backward_refuses_what_it_cannot_do(hostsim_lib):
         forced_tc(None, gn0)
     image = ops.field_prepare_raw(hostsim_lib, spec, table, theta, None)
     assert float(d_table.abs().max()) == 0.0 and float(d_theta.abs().max()) == 0.0      # the refused launch wrote nothing
-    # first-order only (no gradient on the normals: RadF.Geo_enc under dual_field): the same kernel with a zero tangent channel
+    # first-order only (no gradient on the normals: RadF.Geo_enc under dual_field): the single-channel tensor-core kernel
     forced_tc(image, None)
     d_t1, d_th1 = torch.zeros_like(table), torch.zeros_like(theta)
     ops.field_backward_raw(hostsim_lib, spec, table, theta, pts, None, None, g, None, None, None, None, d_t1, d_th1, mode="simt")
