@@ -234,7 +234,6 @@ LS_DEV void ls_level_eval(const ls2fm_field_t& f, int l, const float u[3], float
     const float* tab = f.table + 2 * (size_t)f.levels[l].offset;
     const LsCell c = ls_cell(scale, u);
     float2 v[8];
-#pragma unroll
     uint32_t ci[8];
     ls_corner_indices<0, 8>(res, size, hashed, c, ci);
 #pragma unroll
@@ -325,8 +324,8 @@ __global__ void __launch_bounds__(512, 1) ls_field_forward_kernel(const LsFieldA
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int K = a.f.n_layers, L = a.f.n_levels;
-    const int din0 = a.f.dims[0], dout = a.f.dims[K];
-    const float sp_beta = a.f.softplus_beta, sp_thr = a.f.softplus_threshold;
+    const int dout = a.f.dims[K];
+    const float sp_beta = a.f.softplus_beta;
     float* E = smem + a.net.warp_base + warp * a.net.warp_stride;
     float* A = E + LS_WS * LS_EROWS;                  // A_k = A + (k-1) * 8 * 64, k = 1..K-1
     float* Y = A + LS_WS * LS_H * (K - 1);
